@@ -1,0 +1,155 @@
+/*
+ * nuhtc_b200.h -- C ABI of libnuhtc_b200.so: the B200 (sm_100a) RoI stage + merge of NuHTC.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (passed as void*,
+ * a cudaStream_t).  No entry point allocates device memory or synchronises the stream unless
+ * its comment says so: the caller owns inputs, outputs and workspaces (sizes come from the
+ * *_workspace_bytes helpers).  All return 0 on success or a negative NUHTC_E* code;
+ * nuhtc_last_error() gives a thread-local message for the last failure.
+ *
+ * The reference interface each entry point replaces is cited as file:line under
+ * /root/reference (boyden/NuHTC).  mmcv-full 1.7.2 itself is not vendored there; its FFI
+ * (`ext_module.roi_align_forward`, `ext_module.nms`) is what these mirror.
+ */
+#ifndef NUHTC_B200_H
+#define NUHTC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUHTC_OK 0
+#define NUHTC_EINVAL (-1)     /* bad argument */
+#define NUHTC_ECUDA (-2)      /* a CUDA runtime call or launch failed */
+#define NUHTC_EWORKSPACE (-3) /* workspace too small */
+#define NUHTC_EOVERFLOW (-4)  /* a device-side capacity bound was exceeded (see status words) */
+
+#define NUHTC_MAX_LEVELS 8
+
+int nuhtc_abi_version(void);
+const char *nuhtc_last_error(void);
+
+/* ---- layout ------------------------------------------------------------------------------
+ * FPN levels arrive NCHW fp32 (the mmcv contract).  The RoIAlign gather wants the channel axis
+ * contiguous, so each level is re-laid out once per batch: in [B,C,H,W] -> out [B,H,W,C]. */
+int nuhtc_nchw_to_nhwc(const float *in, float *out, int B, int C, int H, int W, void *stream);
+
+/* ---- RoIAlign ------------------------------------------------------------------------------
+ * Replaces mmcv `ext_module.roi_align_forward(input, rois, output, argmax_y, argmax_x,
+ * pooled_height, pooled_width, spatial_scale, sampling_ratio, pool_mode='avg', aligned)` as
+ * called per level by mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:79,
+ * 96,103 and nuhtc/models/roi_extractors_cus.py:198,218 -- but for ALL levels in one launch.
+ *
+ *   feats[l]   device pointer of level l, fp32, layout NUHTC_LAYOUT_*; H[l], W[l], scale[l]
+ *              (= 1/stride) are host arrays of length L (1..NUHTC_MAX_LEVELS)
+ *   rois       [K,5] fp32 (batch_idx, x1, y1, x2, y2), device
+ *   out        [K,C,PH,PW] fp32, device, caller-allocated, fully overwritten
+ *   mode       NUHTC_ROI_ROUTE: each RoI is pooled on ONE level chosen like
+ *              SingleRoIExtractor.map_roi_levels (single_level_roi_extractor.py:36-55) with
+ *              `finest_scale`; L==1 degenerates to a plain roi_align.
+ *              NUHTC_ROI_SUM: every RoI is pooled on every level and the results are summed in
+ *              level order (AttentionRoIExtractor, roi_extractors_cus.py:213-218,246).
+ *   impl       NUHTC_IMPL_AUTO picks the separable fast kernel when its preconditions hold
+ *              (NHWC, C%4==0, PH==PW in {7,14}); NUHTC_IMPL_DIRECT forces the literal
+ *              per-sample kernel (either layout, any shape), which follows the reference's
+ *              accumulation order exactly. */
+#define NUHTC_LAYOUT_NCHW 0
+#define NUHTC_LAYOUT_NHWC 1
+#define NUHTC_ROI_ROUTE 0
+#define NUHTC_ROI_SUM 1
+#define NUHTC_IMPL_AUTO 0
+#define NUHTC_IMPL_DIRECT 1
+int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const int *W, const float *scale, int L,
+                        int B, int C, int layout, const float *rois, int K, int PH, int PW,
+                        int sampling_ratio, int aligned, int mode, float finest_scale, int impl, float *out,
+                        void *stream);
+
+/* ---- NMS -----------------------------------------------------------------------------------
+ * Replaces mmcv `ext_module.nms(boxes, scores, iou_threshold, offset)` and the class-offset
+ * arithmetic of mmcv.ops.batched_nms (call sites nuhtc/models/bbox_head.py:93,208;
+ * nuhtc/core/post_processing/bbox_nms.py:83; mmdet/core/post_processing/bbox_nms.py:86;
+ * mmdet/models/dense_heads/rpn_head.py:232), batched over independent groups (images).
+ *
+ *   boxes [N,4] fp32, scores [N] fp32, device.
+ *   labels [N] int64 or NULL; groups [N] int32 or NULL (NULL = one group).  Only boxes of the
+ *          same group interact.  Groups must be < num_groups.
+ *   mode   NUHTC_NMS_AGNOSTIC : IoU on the raw coordinates (labels ignored).
+ *          NUHTC_NMS_OFFSET   : coordinates + float(label)*(max_coord_of_group+1) in fp32, all
+ *                               pairs tested (batched_nms below split_thr).
+ *          NUHTC_NMS_PERCLASS : same offset coordinates, only same-label pairs tested
+ *                               (batched_nms at/above split_thr: one nms per class).
+ *   Suppression test: inter/(area_i+area_j-inter) > iou_thr with IEEE fp32 division, areas
+ *   (x2-x1+offset)*(y2-y1+offset); order = score descending, ties lower index first.
+ *   max_group_size  upper bound on the number of boxes in any one group (N if unknown).
+ *   keep   [N] int64 out: group g's kept ORIGINAL indices, score-descending, are
+ *          keep[group_start[g] .. group_start[g]+group_count[g])
+ *   group_start, group_count  [num_groups] int64 out (device)
+ *   status [1] int32 out (device): 0 ok, 1 = a group exceeded max_group_size.
+ *   ws/ws_bytes from nuhtc_nms_workspace_bytes(N, num_groups, max_group_size). */
+#define NUHTC_NMS_AGNOSTIC 0
+#define NUHTC_NMS_OFFSET 1
+#define NUHTC_NMS_PERCLASS 2
+#define NUHTC_NMS_PERCLASS_RAW 3 /* raw coordinates, only same-label pairs: batched_nms(class_agnostic=True) at/above split_thr */
+size_t nuhtc_nms_workspace_bytes(int64_t N, int num_groups, int64_t max_group_size);
+int nuhtc_nms(const float *boxes, const float *scores, const int64_t *labels, const int32_t *groups, int64_t N,
+              int num_groups, int64_t max_group_size, float iou_thr, int offset, int mode, int64_t *keep,
+              int64_t *group_start, int64_t *group_count, int32_t *status, void *ws, size_t ws_bytes,
+              void *stream);
+
+/* ---- mask paste ----------------------------------------------------------------------------
+ * Replaces `_do_paste_mask(masks, boxes, img_h, img_w, skip_empty=False)` + the `>= thr`
+ * of FCNMaskHead.get_seg_masks (mmdet/models/roi_heads/mask_heads/fcn_mask_head.py:344-412,
+ * 292-306): bilinear resample (grid_sample, zeros padding, align_corners=False) of each
+ * [mh,mw] probability map into the image frame under its box.
+ *   probs [N,mh,mw] fp32 (already sigmoid), boxes [N,4] fp32 (x0,y0,x1,y1 in image px).
+ *   out_kind NUHTC_PASTE_PROB : out fp32  [N,img_h,img_w]  resampled probabilities
+ *            NUHTC_PASTE_BIN  : out uint8 [N,img_h,img_w]  (prob >= thr), 0/1  (the dense contract)
+ *            NUHTC_PASTE_BITS : out uint64 [N,img_h,ceil(img_w/64)] bit x%64 of word x/64
+ *   area  [N] int32 or NULL: number of set pixels per mask (BIN/BITS kinds)
+ *   bbox  [N,4] int32 or NULL: tight x0,y0,x1,y1 (exclusive max) of set pixels; 0,0,0,0 if empty */
+#define NUHTC_PASTE_PROB 0
+#define NUHTC_PASTE_BIN 1
+#define NUHTC_PASTE_BITS 2
+int nuhtc_paste_masks(const float *probs, const float *boxes, int N, int mh, int mw, int img_h, int img_w,
+                      float thr, int out_kind, void *out, int32_t *area, int32_t *bbox, void *stream);
+
+/* ---- per-tile mask NMS -----------------------------------------------------------------------
+ * Replaces `mask_nms(masks, pred_scores, thr)` of tools/infer_wsi.py:60-84 (pycocotools
+ * rleEncode + rleIou + the greedy double loop), batched over tiles.
+ *   nuhtc_pack_masks: dense uint8 masks [n,h,w] -> bit rows [n,h,ceil(w/64)] + area + bbox.
+ *   nuhtc_mask_nms:   bits/area/bbox as above, scores [n] fp32, tile [n] int32 or NULL (tile id
+ *                     per mask, < num_tiles; only masks of one tile interact).
+ *                     IoU = |A&B| / |A|B| as double, suppressed when IoU > thr (double compare).
+ *                     Order: score descending, ties higher index first (np.argsort(...)[::-1]).
+ *   keep [n] int32 out, tile_start/tile_count [num_tiles] int32 out: tile t's kept ORIGINAL
+ *   indices in score order are keep[tile_start[t] .. +tile_count[t]). */
+int nuhtc_pack_masks(const uint8_t *masks, int n, int h, int w, uint64_t *bits, int32_t *area, int32_t *bbox,
+                     void *stream);
+size_t nuhtc_mask_nms_workspace_bytes(int n, int num_tiles, int max_tile_size);
+int nuhtc_mask_nms(const uint64_t *bits, const int32_t *area, const int32_t *bbox, const float *scores,
+                   const int32_t *tile, int n, int num_tiles, int max_tile_size, int h, int w, double thr,
+                   int32_t *keep, int32_t *tile_start, int32_t *tile_count, int32_t *status, void *ws,
+                   size_t ws_bytes, void *stream);
+
+/* ---- cross-tile polygon merge ------------------------------------------------------------------
+ * Replaces `merge_overlap(cells, overlap_threshold, merge_strategy)` of
+ * tools/nuclei_merge.py:62-174 (shapely STRtree candidates + polygon IoU + greedy in score
+ * order) on flat arrays.
+ *   xy [sumV,2] fp64 ring vertices, voff [N+1] int64 ring offsets, score [N] fp64 (device).
+ *   strategy 0 'probability', 1 'area'.
+ *   keep_ids [N] int64 out: ORIGINAL indices of kept nuclei ordered by score rank
+ *            (position r = nuclei_id r, nuclei_merge.py:201); num_keep [1] int64 out (device).
+ *   status [1] int32 out: 0 ok, 1 candidate-pair capacity exceeded (retry with larger max_pairs).
+ * This call SYNCHRONISES the stream internally between its phases (it sizes its pair list). */
+size_t nuhtc_merge_workspace_bytes(int64_t N, int64_t sumV, int64_t max_pairs);
+int nuhtc_merge(const double *xy, const int64_t *voff, const double *score, int64_t N, int64_t sumV,
+                double thr, int strategy, int64_t max_pairs, int64_t *keep_ids, int64_t *num_keep,
+                int32_t *status, void *ws, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUHTC_B200_H */

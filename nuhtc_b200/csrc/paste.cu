@@ -1,0 +1,239 @@
+// Mask paste for sm_100a: fused bilinear resample + threshold + store (uint8 / bit rows / fp32).
+//
+// Replaces `_do_paste_mask(masks, boxes, img_h, img_w, skip_empty=False)` followed by
+// `(masks_chunk >= threshold).to(bool)` of FCNMaskHead.get_seg_masks
+//   /root/reference/thirdparty/mmdetection/mmdet/models/roi_heads/mask_heads/fcn_mask_head.py:292-306,344-412
+// without materialising the [N,H,W,2] sampling grid or the fp32 [N,H,W] intermediate: the
+// normalised coordinate of every output pixel is recomputed from the box in the reference's own
+// float op order, and ATen's grid_sampler_2d (bilinear, zeros padding, align_corners=False) is
+// applied in registers.  One CTA owns one mask: the [mh,mw] probability map is staged in shared
+// memory only if the box touches the image; every thread then produces 16 output pixels per step
+// and leaves through a 128-bit streaming store.  Outside the box's reach the result is exactly
+// zero (zeros padding), so most of the kernel is a store stream -- HBM-write bound.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kPasteThreads = 256;
+constexpr int kMaxMaskElems = 64 * 64; // staged probability map (28x28 in every NuHTC config)
+
+// normalised grid coordinate of pixel centre p+0.5 for a box side [a0,a1] (fcn_mask_head.py:388-400)
+__device__ __forceinline__ float grid_coord(int p, float a0, float a1) {
+    float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn((float)p + 0.5f, a0), __fsub_rn(a1, a0)), 2.0f), 1.0f);
+    if (isinf(g)) g = 0.f;
+    return g;
+}
+// ATen grid_sampler unnormalize, align_corners=False: ((g + 1) * size - 1) / 2
+__device__ __forceinline__ float unnormalize(float g, int size) {
+    return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f), 0.5f);
+}
+
+struct AxisTap {
+    int i0;      // floor index; i0+1 is the other tap
+    float w0, w1; // weights of i0 and i0+1
+};
+__device__ __forceinline__ AxisTap axis_tap(int p, float a0, float a1, int size) {
+    const float s = unnormalize(grid_coord(p, a0, a1), size);
+    const float f = floorf(s);
+    AxisTap t;
+    // NaN (degenerate box) or far-away coordinates: push the taps out of range => contributes 0
+    t.i0 = (s >= -2.0f && s <= (float)size + 1.0f) ? (int)f : -4;
+    t.w1 = __fsub_rn(s, f);
+    t.w0 = __fsub_rn(__fadd_rn(f, 1.0f), s);
+    return t;
+}
+
+__device__ __forceinline__ float sample(const float *m, int mh, int mw, const AxisTap ty, const AxisTap tx) {
+    float v = 0.f;
+    const bool y0 = ty.i0 >= 0 && ty.i0 < mh, y1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < mh;
+    const bool x0 = tx.i0 >= 0 && tx.i0 < mw, x1 = tx.i0 + 1 >= 0 && tx.i0 + 1 < mw;
+    if (y0 && x0) v += m[ty.i0 * mw + tx.i0] * (tx.w0 * ty.w0);
+    if (y0 && x1) v += m[ty.i0 * mw + tx.i0 + 1] * (tx.w1 * ty.w0);
+    if (y1 && x0) v += m[(ty.i0 + 1) * mw + tx.i0] * (tx.w0 * ty.w1);
+    if (y1 && x1) v += m[(ty.i0 + 1) * mw + tx.i0 + 1] * (tx.w1 * ty.w1);
+    return v;
+}
+
+// conservative pixel range [lo,hi) outside of which every sample is exactly zero
+__device__ __forceinline__ void active_range(float a0, float a1, int size, int extent, int &lo, int &hi) {
+    const float side = a1 - a0;
+    if (!(side > 0.f) || isinf(side)) { // degenerate / NaN box: evaluate everything literally
+        lo = 0;
+        hi = extent;
+        return;
+    }
+    const float pad = side / (float)size + 2.0f; // half a mask pixel would do; be generous
+    const float l = floorf(a0 - pad), h = ceilf(a1 + pad);
+    lo = l < 0.f ? 0 : (l > (float)extent ? extent : (int)l);
+    hi = h < 0.f ? 0 : (h > (float)extent ? extent : (int)h);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kPasteThreads) paste_kernel(const float *__restrict__ probs, const float *__restrict__ boxes,
+                                                              int mh, int mw, int H, int W, float thr, void *__restrict__ outv,
+                                                              int32_t *__restrict__ area, int32_t *__restrict__ bbox) {
+    __shared__ float s_m[kMaxMaskElems];
+    __shared__ int s_red[5][kPasteThreads / 32];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const float bx0 = boxes[4 * n], by0 = boxes[4 * n + 1], bx1 = boxes[4 * n + 2], by1 = boxes[4 * n + 3];
+    int ax0, ax1, ay0, ay1;
+    active_range(bx0, bx1, mw, W, ax0, ax1);
+    active_range(by0, by1, mh, H, ay0, ay1);
+    if (!(thr > 0.f)) { // 0 >= thr holds for the zero padding too: every pixel must be evaluated
+        ax0 = ay0 = 0;
+        ax1 = W;
+        ay1 = H;
+    }
+    const bool any = ax1 > ax0 && ay1 > ay0;
+    if (any) {
+        const float *src = probs + (size_t)n * mh * mw;
+        for (int i = tid; i < mh * mw; i += kPasteThreads) s_m[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    int cnt = 0, minx = 1 << 30, miny = 1 << 30, maxx = -1, maxy = -1;
+
+    if (KIND == NUHTC_PASTE_BITS) {
+        const int wpr = (W + 63) / 64;
+        unsigned long long *out = (unsigned long long *)outv + (size_t)n * H * wpr;
+        for (int i = tid; i < H * wpr; i += kPasteThreads) {
+            const int y = i / wpr, xw = (i - y * wpr) * 64;
+            unsigned long long word = 0ull;
+            if (any && y >= ay0 && y < ay1 && xw < ax1 && xw + 64 > ax0) {
+                const AxisTap ty = axis_tap(y, by0, by1, mh);
+                const int xa = max(xw, ax0), xb = min(min(xw + 64, ax1), W);
+                for (int x = xa; x < xb; ++x) {
+                    const float v = sample(s_m, mh, mw, ty, axis_tap(x, bx0, bx1, mw));
+                    if (v >= thr) {
+                        word |= 1ull << (x - xw);
+                        minx = min(minx, x);
+                        maxx = max(maxx, x);
+                    }
+                }
+                if (word) {
+                    cnt += __popcll(word);
+                    miny = min(miny, y);
+                    maxy = max(maxy, y);
+                }
+            }
+            out[i] = word;
+        }
+    } else {
+        // 16 pixels (KIND BIN: 16 bytes) or 4 pixels (KIND PROB: 16 bytes) per thread per step
+        constexpr int PX = KIND == NUHTC_PASTE_BIN ? 16 : 4;
+        const size_t total = (size_t)H * W;
+        char *outb = (char *)outv + (size_t)n * total * (KIND == NUHTC_PASTE_BIN ? 1 : 4);
+        const bool vec_ok = (W % PX == 0) && (((uintptr_t)outb) % 16 == 0);
+        if (vec_ok) {
+            const int segs_per_row = W / PX;
+            for (int i = tid; i < H * segs_per_row; i += kPasteThreads) {
+                const int y = i / segs_per_row, xs = (i - y * segs_per_row) * PX;
+                float v[PX];
+#pragma unroll
+                for (int u = 0; u < PX; ++u) v[u] = 0.f;
+                const bool live = any && y >= ay0 && y < ay1 && xs < ax1 && xs + PX > ax0;
+                if (live) {
+                    const AxisTap ty = axis_tap(y, by0, by1, mh);
+#pragma unroll
+                    for (int u = 0; u < PX; ++u) v[u] = sample(s_m, mh, mw, ty, axis_tap(xs + u, bx0, bx1, mw));
+                }
+                if (KIND == NUHTC_PASTE_BIN) {
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+                    if (live) {
+#pragma unroll
+                        for (int u = 0; u < PX; ++u) {
+                            if (v[u] >= thr) {
+                                w[u >> 2] |= 1u << (8 * (u & 3));
+                                ++cnt;
+                                minx = min(minx, xs + u);
+                                maxx = max(maxx, xs + u);
+                                miny = min(miny, y);
+                                maxy = max(maxy, y);
+                            }
+                        }
+                    }
+                    st_stream_u4(outb + (size_t)i * 16, make_uint4(w[0], w[1], w[2], w[3]));
+                } else {
+                    st_stream_f4((float *)outb + (size_t)i * 4, make_float4(v[0], v[1], v[2], v[3]));
+                }
+            }
+        } else {
+            for (size_t i = tid; i < total; i += kPasteThreads) {
+                const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+                float v = 0.f;
+                if (any && y >= ay0 && y < ay1 && x >= ax0 && x < ax1)
+                    v = sample(s_m, mh, mw, axis_tap(y, by0, by1, mh), axis_tap(x, bx0, bx1, mw));
+                if (KIND == NUHTC_PASTE_BIN) {
+                    const bool on = any && v >= thr && y >= ay0 && y < ay1 && x >= ax0 && x < ax1;
+                    ((uint8_t *)outb)[i] = on ? 1 : 0;
+                    if (on) {
+                        ++cnt;
+                        minx = min(minx, x);
+                        maxx = max(maxx, x);
+                        miny = min(miny, y);
+                        maxy = max(maxy, y);
+                    }
+                } else {
+                    ((float *)outb)[i] = v;
+                }
+            }
+        }
+    }
+
+    if (KIND != NUHTC_PASTE_PROB && (area || bbox)) {
+        const int lane = tid & 31, warp = tid >> 5;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        minx = __reduce_min_sync(0xffffffffu, minx);
+        miny = __reduce_min_sync(0xffffffffu, miny);
+        maxx = __reduce_max_sync(0xffffffffu, maxx);
+        maxy = __reduce_max_sync(0xffffffffu, maxy);
+        if (lane == 0) {
+            s_red[0][warp] = cnt;
+            s_red[1][warp] = minx;
+            s_red[2][warp] = miny;
+            s_red[3][warp] = maxx;
+            s_red[4][warp] = maxy;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int c = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+            for (int w = 0; w < kPasteThreads / 32; ++w) {
+                c += s_red[0][w];
+                x0 = min(x0, s_red[1][w]);
+                y0 = min(y0, s_red[2][w]);
+                x1 = max(x1, s_red[3][w]);
+                y1 = max(y1, s_red[4][w]);
+            }
+            if (area) area[n] = c;
+            if (bbox) {
+                bbox[4 * n + 0] = c ? x0 : 0;
+                bbox[4 * n + 1] = c ? y0 : 0;
+                bbox[4 * n + 2] = c ? x1 + 1 : 0;
+                bbox[4 * n + 3] = c ? y1 + 1 : 0;
+            }
+        }
+    }
+}
+
+} // namespace
+
+NUHTC_API int nuhtc_paste_masks(const float *probs, const float *boxes, int N, int mh, int mw, int img_h, int img_w, float thr,
+                                int out_kind, void *out, int32_t *area, int32_t *bbox, void *stream) {
+    NUHTC_CHECK_ARG(N >= 0 && mh >= 1 && mw >= 1 && img_h >= 1 && img_w >= 1, "paste: bad sizes");
+    NUHTC_CHECK_ARG(mh * mw <= kMaxMaskElems, "paste: mask %dx%d larger than the staged maximum", mh, mw);
+    NUHTC_CHECK_ARG(out_kind >= NUHTC_PASTE_PROB && out_kind <= NUHTC_PASTE_BITS, "paste: bad out_kind %d", out_kind);
+    if (N == 0) return NUHTC_OK;
+    NUHTC_CHECK_ARG(probs && boxes && out, "paste: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (out_kind) {
+        case NUHTC_PASTE_PROB:
+            paste_kernel<NUHTC_PASTE_PROB><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
+            break;
+        case NUHTC_PASTE_BIN:
+            paste_kernel<NUHTC_PASTE_BIN><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
+            break;
+        default:
+            paste_kernel<NUHTC_PASTE_BITS><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
+    }
+    NUHTC_LAUNCH_CHECK();
+    return NUHTC_OK;
+}

@@ -1,0 +1,275 @@
+"""Drop-in mirrors of the mmcv.ops surface NuHTC's RoI stage uses, backed by libnuhtc_b200.so.
+
+Signatures, argument meaning and error behaviour follow mmcv-full 1.7.2
+(``mmcv.ops.RoIAlign`` / ``roi_align`` / ``nms`` / ``batched_nms``) as the reference calls them:
+  * RoIAlign built by ``layer_cls(spatial_scale=1/s, **cfg)`` --
+    /root/reference/thirdparty/mmdetection/mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:54-60
+  * ``roi_align(...)`` called positionally -- /root/reference/nuhtc/core/masks/structures.py:48-50
+  * ``batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic)`` --
+    /root/reference/nuhtc/models/bbox_head.py:93,208
+Forward (inference) only; GPU only.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+__all__ = ["RoIAlign", "roi_align", "nms", "batched_nms", "roi_align_levels", "to_nhwc", "clear_layout_cache",
+           "nms_groups"]
+
+
+def _pair(x) -> Tuple[int, int]:
+    if isinstance(x, (tuple, list)):
+        assert len(x) == 2
+        return int(x[0]), int(x[1])
+    return int(x), int(x)
+
+
+# ----------------------------------------------------------------------------- layout staging
+# The RoIAlign gather wants channel-contiguous (NHWC) levels.  A level that arrives NCHW-contiguous
+# is re-laid out once by our own transpose kernel and remembered while the source tensor is alive
+# and unmodified (the three cascade stages and the mask branch pool from the same FPN outputs).
+_LAYOUT_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_LAYOUT_CACHE_MAX = 8
+
+
+def clear_layout_cache() -> None:
+    _LAYOUT_CACHE.clear()
+
+
+def to_nhwc(x: torch.Tensor, cache: bool = True) -> torch.Tensor:
+    """[B,C,H,W] fp32 CUDA (any strides) -> contiguous [B,H,W,C] buffer (returned as a [B,H,W,C] tensor)."""
+    L.require_cuda(x, "input")
+    assert x.dim() == 4 and x.dtype == torch.float32, "expected a 4-D fp32 feature map"
+    B, C, H, W = x.shape
+    if x.permute(0, 2, 3, 1).is_contiguous():  # already channels_last in memory
+        return x.permute(0, 2, 3, 1)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    key = (x.data_ptr(), x._version, tuple(x.shape), x.device.index)
+    if cache and key in _LAYOUT_CACHE:
+        _LAYOUT_CACHE.move_to_end(key)
+        return _LAYOUT_CACHE[key][1]
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().nuhtc_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C, H, W, L.stream_ptr(x.device)), "nchw_to_nhwc")
+    if cache:
+        _LAYOUT_CACHE[key] = (x, out)  # holding `x` keeps its storage (and so the key) from being recycled
+        while len(_LAYOUT_CACHE) > _LAYOUT_CACHE_MAX:
+            _LAYOUT_CACHE.popitem(last=False)
+    return out
+
+
+def _fast_path_ok(C: int, ph: int, pw: int) -> bool:
+    return ph == pw and ph in (7, 14) and C % 64 == 0
+
+
+def roi_align_levels(feats: Sequence[torch.Tensor], rois: torch.Tensor, output_size, spatial_scales: Sequence[float],
+                     sampling_ratio: int = 0, aligned: bool = True, mode: str = "route", finest_scale: float = 56.0,
+                     impl: str = "auto", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """All FPN levels in ONE launch.
+
+    mode 'route': each RoI is pooled on the level SingleRoIExtractor.map_roi_levels picks
+                  (single_level_roi_extractor.py:36-55); one level = plain roi_align.
+    mode 'sum'  : every RoI is pooled on every level, results summed in level order
+                  (AttentionRoIExtractor's RoIAlign branch, roi_extractors_cus.py:213-218,246).
+    feats: NCHW fp32 CUDA tensors [B,C,H_l,W_l] (NCHW-contiguous or channels_last)."""
+    ph, pw = _pair(output_size)
+    nl = len(feats)
+    assert 1 <= nl <= L.MAX_LEVELS and len(spatial_scales) == nl
+    L.require_cuda(rois, "rois")
+    assert rois.dim() == 2 and rois.size(1) == 5, "rois must have shape [K,5]"
+    B, C = feats[0].shape[0], feats[0].shape[1]
+    K = rois.size(0)
+    dev = feats[0].device
+    rois = rois.to(torch.float32).contiguous()
+    if out is None:
+        out = torch.empty((K, C, ph, pw), dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == (K, C, ph, pw) and out.is_contiguous() and out.dtype == torch.float32
+    if K == 0:
+        return out
+    use_fast = impl == "auto" and _fast_path_ok(C, ph, pw)
+    bufs = []
+    for f in feats:
+        L.require_cuda(f, "feats")
+        assert f.dtype == torch.float32 and f.shape[0] == B and f.shape[1] == C
+        if use_fast:
+            bufs.append(to_nhwc(f))
+        else:
+            bufs.append(f if f.is_contiguous() else f.contiguous())
+    layout = L.LAYOUT_NHWC if use_fast else L.LAYOUT_NCHW
+    ptrs = (ctypes.c_void_p * nl)(*[b.data_ptr() for b in bufs])
+    Hs = (ctypes.c_int * nl)(*[int(f.shape[2]) for f in feats])
+    Ws = (ctypes.c_int * nl)(*[int(f.shape[3]) for f in feats])
+    sc = (ctypes.c_float * nl)(*[float(s) for s in spatial_scales])
+    m = {"route": L.ROI_ROUTE, "sum": L.ROI_SUM}[mode]
+    with torch.cuda.device(dev):
+        rc = L.lib().nuhtc_roi_align_fwd(ptrs, Hs, Ws, sc, nl, B, C, layout, rois.data_ptr(), K, ph, pw, int(sampling_ratio),
+                                         int(bool(aligned)), m, float(finest_scale),
+                                         L.IMPL_AUTO if use_fast else L.IMPL_DIRECT, out.data_ptr(), L.stream_ptr(dev))
+    L.check(rc, "roi_align_fwd")
+    return out
+
+
+def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode="avg", aligned=True):
+    """mmcv.ops.roi_align(input, rois, output_size, spatial_scale, sampling_ratio, pool_mode, aligned)."""
+    if pool_mode != "avg":
+        raise NotImplementedError("nuhtc_b200.roi_align implements pool_mode='avg' (the only mode NuHTC configures)")
+    assert rois.size(1) == 5, "RoI must be (idx, x1, y1, x2, y2)!"
+    return roi_align_levels([input], rois, output_size, [spatial_scale], sampling_ratio, aligned, mode="route")
+
+
+class RoIAlign(nn.Module):
+    """mmcv.ops.RoIAlign(output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg', aligned=True,
+    use_torchvision=False); ``forward(input [N,C,H,W], rois [K,5]) -> [K,C,ph,pw]``."""
+
+    def __init__(self, output_size, spatial_scale: float = 1.0, sampling_ratio: int = 0, pool_mode: str = "avg",
+                 aligned: bool = True, use_torchvision: bool = False):
+        super().__init__()
+        self.output_size = _pair(output_size)
+        self.spatial_scale = float(spatial_scale)
+        self.sampling_ratio = int(sampling_ratio)
+        self.pool_mode = pool_mode
+        self.aligned = aligned
+        self.use_torchvision = use_torchvision
+        if use_torchvision:
+            raise NotImplementedError("use_torchvision=True is not a B200-native path")
+
+    def forward(self, input: torch.Tensor, rois: torch.Tensor) -> torch.Tensor:
+        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.pool_mode, self.aligned)
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(output_size={self.output_size}, spatial_scale={self.spatial_scale}, "
+                f"sampling_ratio={self.sampling_ratio}, pool_mode={self.pool_mode}, aligned={self.aligned}, "
+                f"use_torchvision={self.use_torchvision})")
+
+
+# ----------------------------------------------------------------------------- NMS
+_MODE = {"agnostic": L.NMS_AGNOSTIC, "offset": L.NMS_OFFSET, "perclass": L.NMS_PERCLASS,
+         "perclass_raw": L.NMS_PERCLASS_RAW}
+
+
+def nms_groups(boxes: torch.Tensor, scores: torch.Tensor, labels: Optional[torch.Tensor], groups: Optional[torch.Tensor],
+               num_groups: int, max_group_size: int, iou_threshold: float, offset: int = 0, mode: str = "agnostic"):
+    """Batched greedy NMS over independent groups (images), no host sync.
+
+    Returns (keep [N] int64, group_start [G] int64, group_count [G] int64, status [1] int32), all on the device:
+    group g's kept original indices, score-descending, are keep[group_start[g] : group_start[g]+group_count[g]]."""
+    L.require_cuda(boxes, "boxes")
+    N = boxes.size(0)
+    dev = boxes.device
+    boxes = boxes.to(torch.float32).contiguous()
+    scores = scores.to(torch.float32).contiguous()
+    assert boxes.dim() == 2 and boxes.size(1) == 4 and scores.numel() == N
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    if groups is not None:
+        groups = groups.to(torch.int32).contiguous()
+    max_group_size = max(1, min(int(max_group_size), max(N, 1)))
+    keep = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    gstart = torch.empty(num_groups, dtype=torch.int64, device=dev)
+    gcount = torch.empty(num_groups, dtype=torch.int64, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = L.lib()
+    wsb = lib.nuhtc_nms_workspace_bytes(N, num_groups, max_group_size)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.nuhtc_nms(boxes.data_ptr(), scores.data_ptr(), L.ptr(labels), L.ptr(groups), N, num_groups, max_group_size,
+                           float(iou_threshold), int(offset), _MODE[mode], keep.data_ptr(), gstart.data_ptr(), gcount.data_ptr(),
+                           status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev))
+    L.check(rc, "nms")
+    return keep, gstart, gcount, status
+
+
+def _nms_single(boxes, scores, labels, iou_threshold, offset, mode) -> torch.Tensor:
+    N = boxes.size(0)
+    if N == 0:
+        return torch.empty(0, dtype=torch.int64, device=boxes.device)
+    keep, _, gcount, status = nms_groups(boxes, scores, labels, None, 1, N, iou_threshold, offset, mode)
+    k = int(gcount.item())  # the op returns a data-dependent shape, as mmcv's does
+    return keep[:k]
+
+
+def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
+    """mmcv.ops.nms: returns (dets [k,5], inds [k] int64), score-descending.  Accepts Tensor or ndarray."""
+    assert isinstance(boxes, (torch.Tensor, np.ndarray))
+    assert isinstance(scores, (torch.Tensor, np.ndarray))
+    is_numpy = False
+    if isinstance(boxes, np.ndarray):
+        is_numpy = True
+        boxes = torch.from_numpy(boxes).cuda()
+    if isinstance(scores, np.ndarray):
+        scores = torch.from_numpy(scores).cuda()
+    assert boxes.size(1) == 4
+    assert boxes.size(0) == scores.size(0)
+    assert offset in (0, 1)
+    L.require_cuda(boxes, "boxes")
+    b, s = boxes, scores
+    valid_inds = None
+    if score_threshold > 0:
+        valid_mask = scores > score_threshold
+        b, s = boxes[valid_mask], scores[valid_mask]
+        valid_inds = torch.nonzero(valid_mask, as_tuple=False).squeeze(dim=1)
+    inds = _nms_single(b, s, None, iou_threshold, offset, "agnostic")
+    if max_num > 0:
+        inds = inds[:max_num]
+    if valid_inds is not None:
+        inds = valid_inds[inds]
+    dets = torch.cat((boxes[inds], scores[inds].reshape(-1, 1)), dim=1)
+    if is_numpy:
+        dets = dets.cpu().numpy()
+        inds = inds.cpu().numpy()
+    return dets, inds
+
+
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, nms_cfg: Optional[dict],
+                class_agnostic: bool = False):
+    """mmcv.ops.batched_nms.  The class offset ``idxs * (boxes.max() + 1)`` is applied inside the kernel in
+    the same fp32 arithmetic (it perturbs IoUs at the 1e-4 px level, so it is part of the contract); at or
+    above ``split_thr`` only same-class pairs are tested, exactly like mmcv's per-class loop."""
+    if nms_cfg is None:
+        scores, inds = scores.sort(descending=True, stable=True)
+        boxes = boxes[inds]
+        return torch.cat([boxes, scores[:, None]], -1), inds
+    L.require_cuda(boxes, "boxes")
+    nms_cfg_ = nms_cfg.copy()
+    class_agnostic = nms_cfg_.pop("class_agnostic", class_agnostic)
+    nms_type = nms_cfg_.pop("type", "nms")
+    if nms_type != "nms":
+        raise NotImplementedError(f"nms type {nms_type!r}: NuHTC configures type='nms' only")
+    split_thr = nms_cfg_.pop("split_thr", 10000)
+    iou_threshold = nms_cfg_.pop("iou_threshold")
+    offset = nms_cfg_.pop("offset", 0)
+    score_threshold = nms_cfg_.pop("score_threshold", 0)
+    max_num = nms_cfg_.pop("max_num", -1)
+    if nms_cfg_:
+        raise TypeError(f"unexpected nms_cfg keys {sorted(nms_cfg_)}")
+    assert boxes.size(-1) == 4, "rotated boxes are outside the NuHTC path"
+    b, s, lab = boxes, scores, idxs
+    valid_inds = None
+    if score_threshold > 0:
+        valid_mask = scores > score_threshold
+        b, s, lab = boxes[valid_mask], scores[valid_mask], idxs[valid_mask]
+        valid_inds = torch.nonzero(valid_mask, as_tuple=False).squeeze(dim=1)
+    split = boxes.shape[0] >= split_thr  # mmcv then runs one nms per id in `idxs`, class_agnostic or not
+    if class_agnostic:
+        mode = "perclass_raw" if split else "agnostic"
+    else:
+        mode = "perclass" if split else "offset"
+        # mmcv takes boxes.max() over the tensor it is given, i.e. before any score filtering
+        if valid_inds is not None and b.shape[0] != boxes.shape[0]:
+            raise NotImplementedError("score_threshold together with class offsets is not used by NuHTC")
+    keep = _nms_single(b, s, None if mode == "agnostic" else lab, iou_threshold, offset, mode)
+    if max_num > 0:
+        keep = keep[:max_num]
+    if valid_inds is not None:
+        keep = valid_inds[keep]
+    return torch.cat([boxes[keep], scores[keep][:, None]], -1), keep

@@ -1,0 +1,117 @@
+"""GPU parity: RoIAlign (C-ABI nuhtc_roi_align_fwd through the mmcv-surface mirrors) vs the CPU oracle.
+Tolerance: 1e-5 abs in fp32 (BASELINE.json north_star); the literal kernel must be bit-exact."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _rois(K, B, frame, seed, edge=True):
+    g = torch.Generator().manual_seed(seed)
+    ctr = torch.rand(K, 2, generator=g) * frame
+    wh = 4 + torch.rand(K, 2, generator=g) * 90
+    r = torch.cat([torch.randint(0, B, (K, 1), generator=g).float(), ctr - wh / 2, ctr + wh / 2], 1)
+    if edge:
+        r[0, 1:] = torch.tensor([10., 10., 10., 10.])            # zero-size
+        r[1, 1:] = torch.tensor([-60., -60., frame + 60., frame + 60.])  # larger than the frame
+        r[2, 1:] = torch.tensor([frame - 8., frame - 8., frame + 30., frame + 30.])  # hangs off the corner
+        r[3, 1:] = torch.tensor([4., 4., 12., 12.])               # exactly on pixel centres at stride 4
+        r[4, 1:] = torch.tensor([0., 0., float(frame), float(frame)])  # frame-filling (slow path in the fast kernel)
+        r[5, 1:] = torch.tensor([-500., -500., -400., -400.])      # fully outside
+        r[6, 1:] = torch.tensor([30., 40., 33., 200.])             # thin and tall
+    return r
+
+
+@pytest.mark.parametrize("C", [64, 256, 24])
+@pytest.mark.parametrize("P,sr", [(7, 0), (7, 2), (14, 0), (14, 2)])
+def test_single_level_matches_oracle(oracle, C, P, sr):
+    import nuhtc_b200 as nb
+    torch.manual_seed(1)
+    B, H = 2, 32
+    x = torch.randn(B, C, H, H)
+    rois = _rois(96, B, H * 4, seed=P * 10 + sr)
+    ref = oracle.roi_align(x, rois, P, 0.25, sr)
+    out = nb.roi_align(x.cuda(), rois.cuda(), P, 0.25, sr, "avg", True).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= TOL
+    # the literal kernel follows the reference accumulation order: bit-exact
+    lit = nb.roi_align_levels([x.cuda()], rois.cuda(), P, [0.25], sr, True, impl="direct").cpu()
+    assert torch.equal(lit, ref)
+
+
+def test_module_surface_and_empty():
+    import nuhtc_b200 as nb
+    layer = nb.RoIAlign(output_size=7, spatial_scale=1 / 4, sampling_ratio=2)
+    assert layer.output_size == (7, 7) and layer.sampling_ratio == 2
+    x = torch.randn(1, 64, 16, 16, device="cuda")
+    out = layer(x, torch.zeros(0, 5, device="cuda"))
+    assert out.shape == (0, 64, 7, 7)
+    with pytest.raises(nb.NuhtcError):
+        nb.roi_align(x.cpu(), torch.zeros(1, 5), 7)
+
+
+def test_channels_last_input_and_non_aligned(oracle):
+    import nuhtc_b200 as nb
+    torch.manual_seed(2)
+    x = torch.randn(2, 64, 24, 40)
+    rois = _rois(64, 2, 96, seed=5, edge=False)
+    ref = oracle.roi_align(x, rois, 7, 0.25, 2)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    out = nb.roi_align(xc, rois.cuda(), 7, 0.25, 2).cpu()
+    assert (out - ref).abs().max().item() <= TOL
+    ref0 = oracle.roi_align(x, rois, (5, 3), 0.25, 0, aligned=False)
+    out0 = nb.roi_align(x.cuda(), rois.cuda(), (5, 3), 0.25, 0, "avg", False).cpu()
+    assert torch.equal(out0, ref0)
+
+
+@pytest.mark.parametrize("C", [64, 256])
+@pytest.mark.parametrize("P,sr", [(7, 0), (7, 2), (14, 0)])
+def test_routed_levels_match_single_roi_extractor(oracle, C, P, sr):
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    B = 2
+    feats = synth.fpn_levels(B, C, frame=256, seed=3)
+    rois = synth.proposals(B, 200, "routed", frame=256, seed=4)
+    rois[:, 1:] *= 1.0  # 256 frame: sides up to 512 are clipped -> all four levels are exercised
+    lv = oracle.map_roi_levels(rois, 4)
+    assert len(torch.unique(lv)) >= 3
+    ref = oracle.single_roi_extract(feats, rois, synth.FPN_STRIDES, P, sr)
+    out = nb.roi_align_levels([f.cuda() for f in feats], rois.cuda(), P, [1 / s for s in synth.FPN_STRIDES], sr,
+                              mode="route", finest_scale=56).cpu()
+    assert (out - ref).abs().max().item() <= TOL
+    lit = nb.roi_align_levels([f.cuda() for f in feats], rois.cuda(), P, [1 / s for s in synth.FPN_STRIDES], sr,
+                              mode="route", finest_scale=56, impl="direct").cpu()
+    assert torch.equal(lit, ref)
+
+
+@pytest.mark.parametrize("P,sr", [(7, 2), (14, 0)])
+def test_level_sum_matches_attention_extractor_roialign_branch(oracle, P, sr):
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    B, C = 2, 64
+    feats = synth.fpn_levels(B, C, frame=256, seed=6)[:2]
+    rois = synth.proposals(B, 150, "nuclei", frame=256, seed=7)
+    ref = oracle.sum_roi_extract(feats, rois, synth.FPN_STRIDES[:2], P, sr)
+    out = nb.roi_align_levels([f.cuda() for f in feats], rois.cuda(), P, [1 / 4, 1 / 8], sr, mode="sum").cpu()
+    assert (out - ref).abs().max().item() <= 2 * TOL  # two pooled terms are added
+
+
+def test_full_size_linearity_property():
+    """BASELINE cfg-2 size (B=16, C=256, K=16000): RoIAlign is linear in the feature map."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    B, C = 16, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(B, C, 128, 128, device="cuda", generator=g)
+    b = torch.randn(B, C, 128, 128, device="cuda", generator=g)
+    rois = synth.proposals(B, 1000, "nuclei").cuda()
+    fa = nb.roi_align(a, rois, 7, 0.25, 0)
+    fb = nb.roi_align(b, rois, 7, 0.25, 0)
+    fab = nb.roi_align(a + 2 * b, rois, 7, 0.25, 0)
+    assert fa.shape == (16000, 256, 7, 7)
+    assert (fab - (fa + 2 * fb)).abs().max().item() <= 5e-5
+    # and the fast kernel agrees with the literal kernel on a slice of the same launch shape
+    sub = rois[::40].contiguous()
+    assert (nb.roi_align(a, sub, 7, 0.25, 0) - nb.roi_align_levels([a], sub, 7, [0.25], 0, impl="direct")).abs().max().item() <= TOL
