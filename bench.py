@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- WSI tiles/sec through the RoI stage + merge (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                      # our arm
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1      # reference CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one batch of 16 synthetic 256x256 tiles through the hot path (BASELINE configs[1]): 3 cascade stages of
+multi-level RoIAlign 7x7 on 1000 proposals/tile over a 256-channel FPN (strides 4-32), per-class batched NMS on
+the decoded boxes, RoIAlign 14x14 on the kept detections, mask paste + threshold to the tile frame, per-tile mask
+NMS; after the K steps the nuclei of the K*16 tiles are merged across tile seams once (tools/nuclei_merge.py),
+inside the timed region.  The bbox / mask heads are stock-cuDNN work outside the target: seeded stand-ins supply
+their outputs.  Inputs are resident in HBM for `value`; `e2e` repeats the measurement with pinned HOST buffers
+copied in every step and the results read back.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "wsi_tiles_per_sec_roi_stage_plus_merge"
+UNIT = "tiles/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--tiles", type=int, default=16, help="tiles per batch (per GPU)")
+    p.add_argument("--proposals", type=int, default=1000)
+    p.add_argument("--channels", type=int, default=256)
+    p.add_argument("--max-per-img", type=int, default=500)
+    p.add_argument("--dist", default="routed", choices=["nuclei", "routed"], help="proposal size distribution")
+    p.add_argument("--lane", default="dense", choices=["dense", "bits"], help="paste output: dense uint8 masks or bit rows")
+    p.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    p.add_argument("--cpu-tiles", type=int, default=2, help="tiles in the bounded CPU-baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def stage_config(args):
+    from nuhtc_b200.roi_stage import RoIStageConfig
+    return RoIStageConfig(extractor="single", bbox_sampling_ratio=0, mask_sampling_ratio=0, score_thr=0.05, nms_iou=0.5,
+                          max_per_img=args.max_per_img, dense_masks=(args.lane == "dense"))
+
+
+def workload_name(args):
+    return (f"RoI-stage microbench: {args.tiles}x256x256 tiles, {args.proposals} proposals/tile ({args.dist}), "
+            f"{args.channels}-ch FPN strides 4-32, 3 cascade stages 7x7 + 14x14 mask RoIAlign, batched_nms 5 classes, "
+            f"paste+threshold, mask NMS, cross-tile merge")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class EventTimers:
+    """CUDA-event timers on the current stream, keyed by op name."""
+
+    def __init__(self):
+        self.pairs = {}
+        self.enabled = False
+
+    @contextlib.contextmanager
+    def __call__(self, name):
+        if not self.enabled:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.pairs.setdefault(name, []).append((a, b))
+
+    def ms(self):
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.pairs.items()}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def roi_align_bytes(K, C, P, feats, levels_touched):
+    """output written once + every touched level read once + the RoIs."""
+    out = K * C * P * P * 4
+    inp = sum(feats[l].numel() * 4 for l in levels_touched)
+    return out + inp + K * 20
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def cpu_sample(args, nthreads, tiles):
+    """The reference CPU path (oracle port of the mmcv / pycocotools / shapely kernels driven by the reference's
+    per-image flow) on a bounded sample of the same workload: `tiles` tiles through the RoI stage + their share of the merge."""
+    from nuhtc_b200 import synth
+    from oracle import cpu as O
+    from oracle.stage import roi_stage_cpu
+    cfg = stage_config(args)
+    feats = synth.fpn_levels(tiles, args.channels, frame=512, seed=0)
+    rois = synth.proposals(tiles, args.proposals, args.dist, frame=512, seed=0)
+    heads = synth.SyntheticHeads(tiles * args.proposals, seed=0)
+    side = max(1, int(round(tiles ** 0.5)))
+    d = synth.slide_nuclei(side, max(1, tiles // side), per_tile=23, seed=0)
+    t0 = time.perf_counter()
+    roi_stage_cpu(feats, rois, heads.bbox_heads(), heads.mask_head, cfg, nthreads=nthreads)
+    t1 = time.perf_counter()
+    O.merge_overlap_arrays(d["xy"], d["voff"], d["score"], 0.05)
+    t2 = time.perf_counter()
+    return tiles / (t2 - t0), {"roi_stage_s": t1 - t0, "merge_s": t2 - t1}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, parts = cpu_sample(args, cores, args.cpu_tiles)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_tiles / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "tiles_per_step": args.cpu_tiles},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.cpu_tiles} tiles/step through oracle.stage.roi_stage_cpu (RoIAlign/paste split over "
+                                       f"{cores} host threads; NMS / mask NMS / merge single-threaded like mmcv, pycocotools, shapely)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import _lib, synth
+    from nuhtc_b200.roi_stage import RoIStage
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a GPU: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    cfg = stage_config(args)
+    B, C = args.tiles, args.channels
+    K = B * args.proposals
+    # ---- synthetic inputs, generated on the host (pinned: the e2e leg copies them every step)
+    feats_h = [f.pin_memory() for f in synth.fpn_levels(B, C, frame=512, seed=rank)]
+    rois_h = synth.proposals(B, args.proposals, args.dist, frame=512, seed=rank).pin_memory()
+    heads_h = synth.SyntheticHeads(K, seed=rank)
+    feats = [f.to(dev) for f in feats_h]
+    rois = rois_h.to(dev)
+    heads = synth.SyntheticHeads(K, seed=rank).to(dev)
+    stage = RoIStage(cfg, heads.bbox_heads(), heads.mask_head)
+    timers = EventTimers()
+    stage.timer = timers
+    # nuclei of the K*B tiles this rank processes: a stripe of the slide, `B` tiles wide, `steps` tile-rows tall
+    from nuhtc_b200.slide import merge_sharded
+    slide = synth.slide_nuclei(B, args.steps * world, per_tile=23, seed=0)
+    shard = nb.slide.shard_by_rows(slide, rank, world)
+    xy, voff, score = (torch.from_numpy(shard[k]).to(dev) for k in ("xy", "voff", "score"))
+
+    def one_step():
+        nb.clear_layout_cache()  # every batch brings new FPN features: the NHWC staging is part of the step
+        with timers("nchw_to_nhwc"):
+            for f in feats:
+                nb.to_nhwc(f)
+        return stage.run(feats, rois, max_rois_per_tile=args.proposals)
+
+    def merge_step():
+        with timers("merge"):
+            return merge_sharded(xy, voff, score, shard, rank, world, 0.05)
+
+    for _ in range(max(args.warmup, 3)):
+        res = one_step()
+    merge_step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps + the one merge
+    _lib.LAUNCHES["n"] = 0
+    timers.enabled = True
+    timers.pairs = {}
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            res = one_step()
+        kept = merge_step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    timers.enabled = False
+    ms = e0.elapsed_time(e1)
+    launches = _lib.LAUNCHES["n"]
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    total_tiles = args.steps * B * world
+    value = total_tiles / (ms / 1000.0)
+    op_ms = timers.ms()
+
+    # ---- roofline of the dominant kernel: the 7x7 RoIAlign launch (stages 2 and 3 of every step: NHWC staging is
+    # timed separately, so these brackets contain the RoIAlign kernel alone)
+    peak, peak_src = measured_peak_gbs()
+    lv = sorted(set(nb_levels(rois_h)))
+    ra = op_ms.get("roi_align_bbox", [])
+    ra_ms = float(np.mean(ra)) if ra else None
+    alg = roi_align_bytes(K, C, 7, feats_h, lv)
+    roofline = None
+    if ra_ms:
+        ach = alg / (ra_ms * 1e-3) / 1e9
+        roofline = {"kernel": "roi_align_sep_kernel<7,64,1> (7x7 bbox RoIAlign, K=%d, C=%d)" % (K, C), "bound": "hbm",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ra_ms, "launches_timed": len(ra), "peak_source": peak_src}
+    paste = op_ms.get("paste", [])
+    D = int(res.det_boxes.shape[0])
+    extra = {}
+    if paste:
+        pbytes = D * (256 * 256 * (1 if args.lane == "dense" else 0.125) + 28 * 28 * 4 + 16)
+        pms = float(np.mean(paste))
+        extra["paste"] = {"achieved": pbytes / (pms * 1e-3) / 1e9, "unit": "GB/s", "frac": pbytes / (pms * 1e-3) / 1e9 / peak,
+                          "algorithmic_bytes_per_launch": pbytes, "avg_launch_ms": pms, "masks_per_launch": D}
+    rm = op_ms.get("roi_align_mask", [])
+    if rm:
+        mbytes = roi_align_bytes(D, C, 14, feats_h, lv)
+        mms = float(np.mean(rm))
+        extra["roi_align_mask"] = {"achieved": mbytes / (mms * 1e-3) / 1e9, "unit": "GB/s", "frac": mbytes / (mms * 1e-3) / 1e9 / peak,
+                                   "algorithmic_bytes_per_launch": mbytes, "avg_launch_ms": mms}
+    tr = op_ms.get("nchw_to_nhwc", [])
+    if tr:
+        tbytes = 2 * sum(f.numel() * 4 for f in feats_h)
+        tms = float(np.mean(tr))
+        extra["nchw_to_nhwc"] = {"achieved": tbytes / (tms * 1e-3) / 1e9, "unit": "GB/s", "frac": tbytes / (tms * 1e-3) / 1e9 / peak,
+                                 "avg_launch_ms": tms}
+    breakdown = {k: float(np.sum(v)) / args.steps for k, v in op_ms.items()}
+
+    # ---- e2e: pinned host inputs copied every step, results read back every step
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, world, (xy, voff, score, shard, rank))
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, parts = cpu_sample(args, 1, args.cpu_tiles)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_tiles} tiles through oracle.stage.roi_stage_cpu + their merge share, single thread "
+                         f"(roi_stage {parts['roi_stage_s']:.2f}s, merge {parts['merge_s']:.3f}s)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args), "tiles_per_step_per_gpu": B, "proposals_per_tile": args.proposals,
+                           "channels": C, "max_per_img": args.max_per_img, "detections_per_step": D, "mask_lane": args.lane,
+                           "heads": "seeded stand-ins (stock cuDNN heads are outside the target)",
+                           "merge": "once per run over the nuclei of all steps*tiles tiles, inside the timed region",
+                           "nuclei_merged_per_gpu": int(score.numel()), "nuclei_kept": int(kept.numel()) if kept is not None else None,
+                           "l2": "inputs larger than L2 (356 MB FPN levels + 0.8 GB RoIAlign output per launch)",
+                           "parallelism": f"tile stripes over {world} GPU(s), seam nuclei all-gathered for the merge"},
+                "roofline": roofline, "roofline_other": extra, "breakdown_ms_per_step": breakdown, "cpu_baseline": cpu,
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def nb_levels(rois_h, finest=56.0, L=4):
+    """which FPN levels the synthetic RoIs touch (bytes accounting only; same rule as map_roi_levels)"""
+    scale = torch.sqrt((rois_h[:, 3] - rois_h[:, 1]) * (rois_h[:, 4] - rois_h[:, 2]))
+    return torch.floor(torch.log2(scale / finest + 1e-6)).clamp(0, L - 1).long().tolist()
+
+
+def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, world, merge_args):
+    """Same step through the public API with HOST buffers: every step copies the FPN levels, the proposals and the head
+    outputs from pinned host memory and reads the per-tile results back (detections, kept indices, kept bit-row masks)."""
+    import torch.distributed as dist
+    import nuhtc_b200 as nb
+    from nuhtc_b200.slide import merge_sharded
+    steps = args.e2e_steps or min(args.steps, 10)
+    h2d = sum(f.numel() * 4 for f in feats_h) + rois_h.numel() * 4 + sum(t.numel() * 4 for t in heads_h.cls + heads_h.reg)
+    d2h_box = {"n": 0}
+
+    def step():
+        for dst, src in zip(feats, feats_h):
+            dst.copy_(src, non_blocking=True)
+        rois.copy_(rois_h, non_blocking=True)
+        for dst, src in zip(heads.cls + heads.reg, heads_h.cls + heads_h.reg):
+            dst.copy_(src, non_blocking=True)
+        nb.clear_layout_cache()
+        r = stage.run(feats, rois, max_rois_per_tile=args.proposals)
+        nk = int(r.tile_count.sum().item())
+        kept = r.keep[:nk].long()
+        outs = [r.det_boxes[kept], r.det_scores[kept], r.det_labels[kept], r.det_tile[kept], r.mask_bits[kept], r.tile_count]
+        host = [o.cpu() for o in outs]
+        d2h_box["n"] = sum(o.numel() * o.element_size() for o in outs)
+        return host
+
+    for _ in range(2):
+        step()
+    xy, voff, score, shard, rank = merge_args
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    kept = merge_sharded(xy, voff, score, shard, rank, world, 0.05)
+    kept.cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": steps * args.tiles * world / (ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h_box["n"]), "steps": steps, "ms_per_step": ms / steps}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -75,7 +75,9 @@ int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const int *W, c
  *
  *   boxes [N,4] fp32, scores [N] fp32, device.
  *   labels [N] int64 or NULL; groups [N] int32 or NULL (NULL = one group).  Only boxes of the
- *          same group interact.  Groups must be < num_groups.
+ *          same group interact.  Groups must be < num_groups; a NEGATIVE group marks a box that
+ *          is not a candidate at all (e.g. score <= score_thr): it is skipped without a
+ *          host-side compaction.
  *   mode   NUHTC_NMS_AGNOSTIC : IoU on the raw coordinates (labels ignored).
  *          NUHTC_NMS_OFFSET   : coordinates + float(label)*(max_coord_of_group+1) in fp32, all
  *                               pairs tested (batched_nms below split_thr).
@@ -148,6 +150,22 @@ size_t nuhtc_merge_workspace_bytes(int64_t N, int64_t sumV, int64_t max_pairs);
 int nuhtc_merge(const double *xy, const int64_t *voff, const double *score, int64_t N, int64_t sumV,
                 double thr, int strategy, int64_t max_pairs, int64_t *keep_ids, int64_t *num_keep,
                 int32_t *status, void *ws, size_t ws_bytes, void *stream);
+
+/* The two phases of the merge, exposed separately for the multi-GPU merge (nuhtc_b200/seam.py), where the
+ * resolve rounds alternate with an exchange of seam-nucleus states between ranks:
+ *   nuhtc_merge_graph : suppression graph of the N polygons as a CSR keyed by the suppressed nucleus:
+ *                       in_list[in_off[b] .. in_off[b]+indeg[b]) = nuclei that outrank b (score desc, ties lower
+ *                       index) and overlap it with IoU > thr.  indeg [N], in_off [N+1], in_list [max_pairs] int32
+ *                       out (device); *num_pairs (HOST) = candidate pairs examined.  Synchronises the stream.
+ *   nuhtc_merge_rounds: `rounds` sweeps of the greedy fixed-point rule over state [N] uint8
+ *                       (0 undecided, 1 kept, 2 suppressed); nodes with frozen[i] != 0 are read but never written
+ *                       (their state is owned by another rank).  remaining [1] int64 out (device): undecided,
+ *                       non-frozen nodes after the last sweep.  No synchronisation. */
+int nuhtc_merge_graph(const double *xy, const int64_t *voff, const double *score, int64_t N, int64_t sumV,
+                      double thr, int64_t max_pairs, int32_t *indeg, int32_t *in_off, int32_t *in_list,
+                      int64_t *num_pairs, int32_t *status, void *ws, size_t ws_bytes, void *stream);
+int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_t *in_list, int64_t N,
+                       const uint8_t *frozen, uint8_t *state, int64_t *remaining, int rounds, void *stream);
 
 #ifdef __cplusplus
 }

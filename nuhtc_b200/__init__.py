@@ -10,5 +10,6 @@ from .mmcv_ops import RoIAlign, roi_align, nms, batched_nms, roi_align_levels, n
 from .mask_paste import _do_paste_mask, paste_masks, get_seg_masks, get_seg_masks_device
 from .mask_nms import mask_nms, mask_nms_device, pack_masks
 from .nuclei_merge import merge_arrays, merge_overlap
+from . import slide, synth, roi_stage
 
 __version__ = "0.1.0"

@@ -39,6 +39,8 @@ SIGNATURES = {
     "nuhtc_mask_nms": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_merge_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "nuhtc_merge": (_i, [_vp, _vp, _vp, _i64, _i64, _d, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nuhtc_merge_graph": (_i, [_vp, _vp, _vp, _i64, _i64, _d, _i64, _vp, _vp, _vp, _c.POINTER(_i64), _vp, _vp, _sz, _vp]),
+    "nuhtc_merge_rounds": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
 }
 
 _lib = None
@@ -82,3 +84,13 @@ def ptr(t) -> int:
 def require_cuda(t: torch.Tensor, name: str) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise NuhtcError(f"{name} must be a CUDA tensor: nuhtc_b200 ops run on the GPU only (no CPU fallback)")
+
+
+# ---- launch accounting: how many of OUR kernels each C-ABI call enqueues (bench.py reports the sum as
+# "gpu_launches"; library kernels such as cub's radix sort are not counted)
+LAUNCHES = {"n": 0}
+KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "roi_align": 1, "nms": 6, "paste": 1, "pack": 3, "mask_nms": 6, "merge": 16}
+
+
+def count(op: str, n: int = 1) -> None:
+    LAUNCHES["n"] += KERNELS_PER_CALL[op] * n

@@ -95,9 +95,11 @@ __global__ void mnms_prep_kernel(const float *__restrict__ scores, const int32_t
     if (p >= n) return;
     const int i = n - 1 - p;
     int t = tile ? tile[i] : 0;
-    if (t < 0 || t >= T) {
+    if (t < 0) {
+        t = T; // negative tile = filtered-out mask: parked in a trash segment behind every real tile
+    } else if (t >= T) {
         atomicExch(status, 2);
-        t = 0;
+        t = T;
     }
     keys[p] = ((uint64_t)(uint32_t)t << 32) | float_desc_key(scores[i]);
     vals[p] = i;
@@ -208,7 +210,7 @@ static MnmsWs mnms_layout(void *ws, int n, int T, int M) {
     L.vals_out = (int32_t *)take(sizeof(int32_t) * n);
     L.sarea = (int32_t *)take(sizeof(int32_t) * n);
     L.sbbox = (int4 *)take(sizeof(int4) * n);
-    L.cnt = (int *)take(sizeof(int) * T);
+    L.cnt = (int *)take(sizeof(int) * (T + 1));
     L.seg_start = (int *)take(sizeof(int) * (T + 1));
     L.mask = (uint64_t *)take(sizeof(uint64_t) * (size_t)n * wpr);
     size_t bytes = 0;
@@ -274,11 +276,11 @@ NUHTC_API int nuhtc_mask_nms(const uint64_t *bits, const int32_t *area, const in
     const int wpm = (w + 63) / 64;
     NUHTC_CHECK_ARG(wpr <= 65535, "mask_nms: max_tile_size too large");
     const int nb = (n + 255) / 256;
-    mnms_init_kernel<<<(T + 255) / 256, 256, 0, st>>>(L.cnt, T, status);
+    mnms_init_kernel<<<(T + 256) / 256, 256, 0, st>>>(L.cnt, T + 1, status);
     mnms_prep_kernel<<<nb, 256, 0, st>>>(scores, tile, n, T, L.keys_in, L.vals_in, L.cnt, status);
     segments_kernel<int32_t><<<1, 256, 0, st>>>(L.cnt, T, max_tile_size, L.seg_start, tile_start, status);
     int tbits = 0;
-    while ((1 << tbits) < T) ++tbits;
+    while ((1 << tbits) < T + 1) ++tbits;
     size_t cub_bytes = L.cub_bytes;
     NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, n, 0,
                                                32 + tbits, st));

@@ -266,11 +266,13 @@ __global__ void merge_state_init_kernel(const int32_t *__restrict__ indeg, int64
     if (i < N) state[i] = indeg[i] == 0 ? 1 : 0;
 }
 
+// `frozen` (nullable): nodes whose state is owned elsewhere (halo copies in the multi-GPU merge) are only read
 __global__ void merge_round_kernel(const int32_t *__restrict__ in_off, const int32_t *__restrict__ indeg,
-                                   const int32_t *__restrict__ in_list, int64_t N, volatile uint8_t *state,
-                                   int64_t *remaining) {
+                                   const int32_t *__restrict__ in_list, int64_t N, const uint8_t *__restrict__ frozen,
+                                   volatile uint8_t *state, int64_t *remaining) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N || state[i] != 0) return;
+    if (frozen && frozen[i]) return;
     bool all_sup = true, any_kept = false;
     const int o = in_off[i];
     for (int k = 0; k < indeg[i]; ++k) {
@@ -420,34 +422,12 @@ __global__ void merge_order64_kernel(const int32_t *__restrict__ order, int64_t 
 
 } // namespace
 
-NUHTC_API size_t nuhtc_merge_workspace_bytes(int64_t N, int64_t sumV, int64_t max_pairs) {
-    (void)sumV;
-    if (N <= 0) return 256;
-    if (max_pairs < 1) max_pairs = 1;
-    return merge_layout(nullptr, N, max_pairs).total;
-}
-
-NUHTC_API int nuhtc_merge(const double *xy, const int64_t *voff, const double *score, int64_t N, int64_t sumV, double thr,
-                          int strategy, int64_t max_pairs, int64_t *keep_ids, int64_t *num_keep, int32_t *status, void *ws,
-                          size_t ws_bytes, void *stream) {
-    (void)sumV;
-    NUHTC_CHECK_ARG(N >= 0 && N < (1ll << 31) - 1, "merge: N out of range");
-    NUHTC_CHECK_ARG(strategy == 0 || strategy == 1, "merge: strategy must be 0 (probability) or 1 (area)");
-    NUHTC_CHECK_ARG(thr >= 0.0, "merge: overlap_threshold must be >= 0");
-    NUHTC_CHECK_ARG(num_keep && status, "merge: null output pointer");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (N == 0) {
-        NUHTC_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st));
-        NUHTC_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
-        return NUHTC_OK;
-    }
-    NUHTC_CHECK_ARG(xy && voff && score && keep_ids && ws, "merge: null pointer");
-    if (max_pairs < 1) max_pairs = 1;
-    MergeWs L = merge_layout(ws, N, max_pairs);
-    if (L.total > ws_bytes) {
-        nuhtc_set_error("merge: workspace %zu < required %zu", ws_bytes, L.total);
-        return NUHTC_EWORKSPACE;
-    }
+// Builds the suppression graph of the N polygons: CSR by suppressed node (in_off/in_list = its higher-ranked
+// suppressors), plus the rank order.  Graph arrays may live in the workspace (single-GPU merge) or be
+// caller-provided (nuhtc_merge_graph).  Synchronises the stream twice (grid sizing, pair count).
+static int build_graph(MergeWs &L, const double *xy, const int64_t *voff, const double *score, int64_t N, double thr,
+                       int64_t max_pairs, int32_t *indeg, int32_t *in_off, int32_t *in_list, int64_t *npairs_out,
+                       int32_t *status, cudaStream_t st) {
     const unsigned nb = (unsigned)((N + 255) / 256);
     merge_init_kernel<<<1, 1, 0, st>>>(L.ext, L.counters, status);
     merge_stats_kernel<<<nb, 256, 0, st>>>(xy, voff, score, N, L.env, L.area2, L.keys_in, L.vals_in, L.ext);
@@ -485,37 +465,123 @@ NUHTC_API int nuhtc_merge(const double *xy, const int64_t *voff, const double *s
     int64_t npairs = 0;
     NUHTC_CUDA(cudaMemcpyAsync(&npairs, L.poff + N, 8, cudaMemcpyDeviceToHost, st));
     NUHTC_CUDA(cudaStreamSynchronize(st));
+    *npairs_out = npairs;
     if (npairs > max_pairs) {
         const int32_t one = 1;
         NUHTC_CUDA(cudaMemcpyAsync(status, &one, 4, cudaMemcpyHostToDevice, st));
-        NUHTC_CUDA(cudaMemcpyAsync(num_keep, &npairs, 8, cudaMemcpyHostToDevice, st)); // tells the caller what to retry with
         NUHTC_CUDA(cudaStreamSynchronize(st));
         nuhtc_set_error("merge: %lld candidate pairs exceed max_pairs=%lld", (long long)npairs, (long long)max_pairs);
         return NUHTC_EOVERFLOW;
     }
-    NUHTC_CUDA(cudaMemsetAsync(L.indeg, 0, 4 * N, st));
+    NUHTC_CUDA(cudaMemsetAsync(indeg, 0, 4 * N, st));
     NUHTC_CUDA(cudaMemsetAsync(L.cursor, 0, 4 * N, st));
     if (npairs > 0) {
         merge_pairs_kernel<true><<<nb128, 128, 0, st>>>(L.env, L.rank, L.sidx, L.cstart, L.cend, N, g, nullptr, L.poff, max_pairs,
                                                          L.pairs);
         merge_iou_kernel<<<(unsigned)((npairs + kIouWarps - 1) / kIouWarps), kIouWarps * 32, 0, st>>>(xy, voff, L.env, L.area2, L.pairs,
-                                                                                                     npairs, thr, L.sup, L.indeg);
+                                                                                                     npairs, thr, L.sup, indeg);
     }
-    NUHTC_CUDA(cudaMemsetAsync(L.in_off + N, 0, 4, st));
-    // in_off needs indeg[0..N) followed by a 0: scan N+1 items reading indeg then the sentinel
-    NUHTC_CUDA(cudaMemcpyAsync(L.in_off, L.indeg, 4 * N, cudaMemcpyDeviceToDevice, st));
+    NUHTC_CUDA(cudaMemsetAsync(in_off + N, 0, 4, st));
+    NUHTC_CUDA(cudaMemcpyAsync(in_off, indeg, 4 * N, cudaMemcpyDeviceToDevice, st));
     cb = L.cub_bytes;
-    NUHTC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, cb, L.in_off, L.in_off, N + 1, st));
+    NUHTC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, cb, in_off, in_off, N + 1, st));
     if (npairs > 0)
-        merge_fill_in_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(L.pairs, L.sup, npairs, L.in_off, L.cursor, L.in_list);
+        merge_fill_in_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(L.pairs, L.sup, npairs, in_off, L.cursor, in_list);
+    NUHTC_LAUNCH_CHECK();
+    return NUHTC_OK;
+}
+
+NUHTC_API size_t nuhtc_merge_workspace_bytes(int64_t N, int64_t sumV, int64_t max_pairs) {
+    (void)sumV;
+    if (N <= 0) return 256;
+    if (max_pairs < 1) max_pairs = 1;
+    return merge_layout(nullptr, N, max_pairs).total;
+}
+
+static int merge_check_args(const double *xy, const int64_t *voff, const double *score, int64_t N, double thr, void *ws) {
+    NUHTC_CHECK_ARG(N >= 0 && N < (1ll << 31) - 1, "merge: N out of range");
+    NUHTC_CHECK_ARG(thr >= 0.0, "merge: overlap_threshold must be >= 0");
+    NUHTC_CHECK_ARG(N == 0 || (xy && voff && score && ws), "merge: null pointer");
+    return NUHTC_OK;
+}
+
+NUHTC_API int nuhtc_merge_graph(const double *xy, const int64_t *voff, const double *score, int64_t N, int64_t sumV, double thr,
+                                int64_t max_pairs, int32_t *indeg, int32_t *in_off, int32_t *in_list, int64_t *num_pairs,
+                                int32_t *status, void *ws, size_t ws_bytes, void *stream) {
+    (void)sumV;
+    int rc = merge_check_args(xy, voff, score, N, thr, ws);
+    if (rc) return rc;
+    NUHTC_CHECK_ARG(num_pairs && status, "merge_graph: null output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    *num_pairs = 0;
+    if (N == 0) {
+        NUHTC_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+        if (in_off) NUHTC_CUDA(cudaMemsetAsync(in_off, 0, 4, st));
+        return NUHTC_OK;
+    }
+    NUHTC_CHECK_ARG(indeg && in_off && in_list, "merge_graph: null output pointer");
+    if (max_pairs < 1) max_pairs = 1;
+    MergeWs L = merge_layout(ws, N, max_pairs);
+    if (L.total > ws_bytes) {
+        nuhtc_set_error("merge: workspace %zu < required %zu", ws_bytes, L.total);
+        return NUHTC_EWORKSPACE;
+    }
+    return build_graph(L, xy, voff, score, N, thr, max_pairs, indeg, in_off, in_list, num_pairs, status, st);
+}
+
+NUHTC_API int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_t *in_list, int64_t N,
+                                 const uint8_t *frozen, uint8_t *state, int64_t *remaining, int rounds, void *stream) {
+    NUHTC_CHECK_ARG(N >= 0 && rounds >= 1, "merge_rounds: bad sizes");
+    NUHTC_CHECK_ARG(remaining != nullptr, "merge_rounds: null output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) {
+        NUHTC_CUDA(cudaMemsetAsync(remaining, 0, 8, st));
+        return NUHTC_OK;
+    }
+    NUHTC_CHECK_ARG(in_off && indeg && in_list && state, "merge_rounds: null pointer");
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    for (int r = 0; r < rounds; ++r) {
+        if (r == rounds - 1) NUHTC_CUDA(cudaMemsetAsync(remaining, 0, 8, st)); // only the last round's count is meaningful
+        merge_round_kernel<<<nb, 256, 0, st>>>(in_off, indeg, in_list, N, frozen, state, remaining);
+    }
+    NUHTC_LAUNCH_CHECK();
+    return NUHTC_OK;
+}
+
+NUHTC_API int nuhtc_merge(const double *xy, const int64_t *voff, const double *score, int64_t N, int64_t sumV, double thr,
+                          int strategy, int64_t max_pairs, int64_t *keep_ids, int64_t *num_keep, int32_t *status, void *ws,
+                          size_t ws_bytes, void *stream) {
+    (void)sumV;
+    int rc = merge_check_args(xy, voff, score, N, thr, ws);
+    if (rc) return rc;
+    NUHTC_CHECK_ARG(strategy == 0 || strategy == 1, "merge: strategy must be 0 (probability) or 1 (area)");
+    NUHTC_CHECK_ARG(num_keep && status, "merge: null output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) {
+        NUHTC_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st));
+        NUHTC_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+        return NUHTC_OK;
+    }
+    NUHTC_CHECK_ARG(keep_ids != nullptr, "merge: null pointer");
+    if (max_pairs < 1) max_pairs = 1;
+    MergeWs L = merge_layout(ws, N, max_pairs);
+    if (L.total > ws_bytes) {
+        nuhtc_set_error("merge: workspace %zu < required %zu", ws_bytes, L.total);
+        return NUHTC_EWORKSPACE;
+    }
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    int64_t npairs = 0;
+    rc = build_graph(L, xy, voff, score, N, thr, max_pairs, L.indeg, L.in_off, L.in_list, &npairs, status, st);
+    if (rc == NUHTC_EOVERFLOW) {
+        NUHTC_CUDA(cudaMemcpyAsync(num_keep, &npairs, 8, cudaMemcpyHostToDevice, st)); // tells the caller what to retry with
+        NUHTC_CUDA(cudaStreamSynchronize(st));
+    }
+    if (rc) return rc;
     merge_state_init_kernel<<<nb, 256, 0, st>>>(L.indeg, N, L.state);
     // ---- resolve rounds
     for (int guard = 0; guard < (1 << 20); ++guard) {
-        NUHTC_CUDA(cudaMemsetAsync(L.counters, 0, 8, st));
-        for (int r = 0; r < 4; ++r) {
-            if (r == 3) NUHTC_CUDA(cudaMemsetAsync(L.counters, 0, 8, st));
-            merge_round_kernel<<<nb, 256, 0, st>>>(L.in_off, L.indeg, L.in_list, N, L.state, L.counters);
-        }
+        rc = nuhtc_merge_rounds(L.in_off, L.indeg, L.in_list, N, nullptr, L.state, L.counters, 4, stream);
+        if (rc) return rc;
         int64_t remaining = 0;
         NUHTC_CUDA(cudaMemcpyAsync(&remaining, L.counters, 8, cudaMemcpyDeviceToHost, st));
         NUHTC_CUDA(cudaStreamSynchronize(st));
@@ -531,7 +597,7 @@ NUHTC_API int nuhtc_merge(const double *xy, const int64_t *voff, const double *s
     }
     merge_flags_kernel<<<nb, 256, 0, st>>>(L.order, L.state, L.pick_rank, strategy, N, L.flags);
     merge_order64_kernel<<<nb, 256, 0, st>>>(L.order, N, L.order64);
-    cb = L.cub_bytes;
+    size_t cb = L.cub_bytes;
     NUHTC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, cb, L.order64, L.flags, keep_ids, num_keep, N, st));
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;

@@ -52,9 +52,11 @@ __global__ void __launch_bounds__(256) nms_prep_kernel(const float4 *__restrict_
     int m = float_ordered_int(-INFINITY);
     if (live) {
         if (groups) g = groups[i];
-        if (g < 0 || g >= G) {
+        if (g < 0) {
+            g = G; // negative group = "not a candidate": parked in a trash segment behind every real group
+        } else if (g >= G) {
             atomicExch(status, 2);
-            g = 0;
+            g = G;
         }
         keys[i] = ((uint64_t)(uint32_t)g << 32) | float_desc_key(scores[i]);
         vals[i] = (int32_t)i;
@@ -213,8 +215,8 @@ static NmsWs nms_layout(void *ws, int64_t N, int G, int64_t M) {
     L.sbox = (float4 *)take(sizeof(float4) * N);
     L.sarea = (float *)take(sizeof(float) * N);
     L.slab = (int32_t *)take(sizeof(int32_t) * N);
-    L.cnt = (int *)take(sizeof(int) * G);
-    L.gmax = (int *)take(sizeof(int) * G);
+    L.cnt = (int *)take(sizeof(int) * (G + 1));
+    L.gmax = (int *)take(sizeof(int) * (G + 1));
     L.seg_start = (int *)take(sizeof(int) * (G + 1));
     L.mask = (uint64_t *)take(sizeof(uint64_t) * (size_t)N * wpr);
     L.cub_bytes = cub_sort_bytes(N);
@@ -263,12 +265,12 @@ NUHTC_API int nuhtc_nms(const float *boxes, const float *scores, const int64_t *
     NUHTC_CHECK_ARG((size_t)wpr * 8 <= 200 * 1024, "nms: group too large for the shared removed-set");
     const float fo = (float)offset;
     const int nb = (int)((N + 255) / 256);
-    nms_init_kernel<<<(G + 255) / 256, 256, 0, st>>>(L.cnt, L.gmax, G, status);
+    nms_init_kernel<<<(G + 256) / 256, 256, 0, st>>>(L.cnt, L.gmax, G + 1, status);
     nms_prep_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, groups, N, G, mode == NUHTC_NMS_OFFSET || mode == NUHTC_NMS_PERCLASS, L.keys_in,
                                         L.vals_in, L.cnt, L.gmax, status);
     segments_kernel<int64_t><<<1, 256, 0, st>>>(L.cnt, G, max_group_size, L.seg_start, group_start, status);
     int gbits = 0;
-    while ((1 << gbits) < G) ++gbits;
+    while ((1 << gbits) < G + 1) ++gbits;
     size_t cub_bytes = L.cub_bytes;
     NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, N, 0,
                                                32 + gbits, st));

@@ -34,6 +34,7 @@ def pack_masks(masks: torch.Tensor):
             rc = L.lib().nuhtc_pack_masks(masks.data_ptr(), n, h, w, bits.data_ptr(), area.data_ptr(), bbox.data_ptr(),
                                           L.stream_ptr(dev))
         L.check(rc, "pack_masks")
+        L.count("pack")
     return bits, area, bbox
 
 
@@ -62,6 +63,7 @@ def mask_nms_device(bits: torch.Tensor, area: torch.Tensor, bbox: torch.Tensor, 
                                 mts, h, int(width), float(thr), keep.data_ptr(), tstart.data_ptr(), tcount.data_ptr(),
                                 status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev))
     L.check(rc, "mask_nms")
+    L.count("mask_nms")
     return keep, tstart, tcount, status
 
 

@@ -58,6 +58,7 @@ def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int
                                            float(0.0 if thr is None else thr), k, out.data_ptr(), L.ptr(area), L.ptr(bbox),
                                            L.stream_ptr(dev))
         L.check(rc, "paste_masks")
+        L.count("paste")
     return (out, area, bbox) if want_stats else out
 
 

@@ -60,6 +60,7 @@ def to_nhwc(x: torch.Tensor, cache: bool = True) -> torch.Tensor:
     out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         L.check(L.lib().nuhtc_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C, H, W, L.stream_ptr(x.device)), "nchw_to_nhwc")
+    L.count("nchw_to_nhwc")
     if cache:
         _LAYOUT_CACHE[key] = (x, out)  # holding `x` keeps its storage (and so the key) from being recycled
         while len(_LAYOUT_CACHE) > _LAYOUT_CACHE_MAX:
@@ -116,6 +117,7 @@ def roi_align_levels(feats: Sequence[torch.Tensor], rois: torch.Tensor, output_s
                                          int(bool(aligned)), m, float(finest_scale),
                                          L.IMPL_AUTO if use_fast else L.IMPL_DIRECT, out.data_ptr(), L.stream_ptr(dev))
     L.check(rc, "roi_align_fwd")
+    L.count("roi_align")
     return out
 
 
@@ -186,6 +188,7 @@ def nms_groups(boxes: torch.Tensor, scores: torch.Tensor, labels: Optional[torch
                            float(iou_threshold), int(offset), _MODE[mode], keep.data_ptr(), gstart.data_ptr(), gcount.data_ptr(),
                            status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev))
     L.check(rc, "nms")
+    L.count("nms")
     return keep, gstart, gcount, status
 
 

@@ -55,6 +55,7 @@ def merge_arrays(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor, over
             del ws
             continue
         L.check(rc, "merge")
+        L.count("merge")
         break
     else:
         raise L.NuhtcError("merge: candidate-pair capacity could not be satisfied")

@@ -1,0 +1,221 @@
+"""Device-resident HTC RoI stage for a batch of tiles.
+
+Mirrors the control flow of the reference's RoI heads
+  * stock ``HybridTaskCascadeRoIHead.simple_test``  thirdparty/mmdetection/mmdet/models/roi_heads/htc_roi_head.py:330-503
+  * ``HybridTaskCascadeRoIHead_Lite.simple_test``   nuhtc/models/htc_roi_head_cus.py:2184-2376
+followed by the per-tile post-processing of tools/infer_wsi.py:510-526 (margin / min_area filter, mask NMS),
+but keeps every intermediate on the GPU: no per-image Python loop, no ``.cpu().numpy()`` between the mask head
+and the paste, no per-instance D2H.  The ops are the ones in this package (one multi-level
+RoIAlign launch per cascade stage, one grouped NMS launch for all tiles, fused paste, batched mask NMS); the
+bbox / mask heads are callables supplied by the caller (stock PyTorch modules -- outside this package's target).
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from .mask_nms import mask_nms_device, pack_masks
+from .mask_paste import paste_masks
+from .mmcv_ops import nms_groups, roi_align_levels
+
+__all__ = ["RoIStageConfig", "RoIStage", "RoIStageResult", "delta2bbox", "bbox2roi"]
+
+
+@dataclass
+class RoIStageConfig:
+    featmap_strides: Tuple[int, ...] = (4, 8, 16, 32)
+    finest_scale: float = 56.0
+    extractor: str = "single"          # 'single': SingleRoIExtractor routing; 'sum': levels [0, sum_levels) summed
+    sum_levels: int = 2                # AttentionRoIExtractor pools levels 0,1 with RoIAlign (roi_extractors_cus.py:213-218)
+    bbox_out: int = 7
+    bbox_sampling_ratio: int = 0       # stock HTC 0; NuHTC configs use 2
+    mask_out: int = 14
+    mask_sampling_ratio: int = 0
+    num_stages: int = 3
+    stage_stds: Tuple[Tuple[float, ...], ...] = ((0.1, 0.1, 0.2, 0.2), (0.05, 0.05, 0.1, 0.1), (0.033, 0.033, 0.067, 0.067))
+    num_classes: int = 5
+    score_thr: float = 0.05            # stock HTC 0.05; NuHTC 0.35
+    nms_iou: float = 0.5
+    max_per_img: int = 500             # NuHTC PanNuke 500; stock HTC 100
+    mask_thr_binary: float = 0.5
+    img_shape: Tuple[int, int] = (512, 512)   # network frame (tile x scale_factor)
+    ori_shape: Tuple[int, int] = (256, 256)   # tile frame
+    scale_factor: float = 2.0
+    margin: int = 0                    # tools/infer_wsi.py --margin
+    min_area: int = 10                 # tools/infer_wsi.py --min_area
+    mask_nms_thr: float = 0.05         # tools/infer_wsi.py:526
+    dense_masks: bool = True           # True: [D,H,W] uint8 masks as get_seg_masks builds them; False: bit rows only
+
+
+@dataclass
+class RoIStageResult:
+    det_boxes: torch.Tensor      # [D,4] tile-frame boxes of the detections that entered the mask branch
+    det_scores: torch.Tensor     # [D]
+    det_labels: torch.Tensor     # [D] int64
+    det_tile: torch.Tensor       # [D] int32 tile (image) index inside the batch
+    masks: Optional[torch.Tensor]  # [D,H,W] bool (dense_masks) or None
+    mask_bits: torch.Tensor      # [D,H,ceil(W/64)] int64 bit rows
+    mask_area: torch.Tensor      # [D] int32
+    keep: torch.Tensor           # [D] int32: per tile, kept detection indices (into D) in score order
+    tile_start: torch.Tensor     # [B] int32
+    tile_count: torch.Tensor     # [B] int32
+
+    def kept_indices(self) -> List[torch.Tensor]:
+        ts, tc = self.tile_start.cpu().tolist(), self.tile_count.cpu().tolist()
+        return [self.keep[s:s + c].long() for s, c in zip(ts, tc)]
+
+
+def bbox2roi(bbox_list: Sequence[torch.Tensor]) -> torch.Tensor:
+    """mmdet/core/bbox/transforms.py:59-78."""
+    parts = []
+    for img_id, b in enumerate(bbox_list):
+        if b.size(0) > 0:
+            parts.append(torch.cat([b.new_full((b.size(0), 1), img_id), b[:, :4]], dim=-1))
+        else:
+            parts.append(b.new_zeros((0, 5)))
+    return torch.cat(parts, 0)
+
+
+def delta2bbox(rois: torch.Tensor, deltas: torch.Tensor, stds, max_shape=None, means=(0., 0., 0., 0.),
+               wh_ratio_clip: float = 16 / 1000) -> torch.Tensor:
+    """Class-agnostic form of mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:163-260 (same op order)."""
+    if deltas.size(0) == 0:
+        return deltas
+    d = deltas * deltas.new_tensor(stds).view(1, -1) + deltas.new_tensor(means).view(1, -1)
+    pxy = (rois[:, :2] + rois[:, 2:]) * 0.5
+    pwh = rois[:, 2:] - rois[:, :2]
+    dxy_wh = pwh * d[:, :2]
+    max_ratio = abs(math.log(wh_ratio_clip))
+    dwh = d[:, 2:].clamp(min=-max_ratio, max=max_ratio)
+    gxy = pxy + dxy_wh
+    gwh = pwh * dwh.exp()
+    out = torch.cat([gxy - gwh * 0.5, gxy + gwh * 0.5], dim=-1)
+    if max_shape is not None:
+        out[..., 0::2].clamp_(min=0, max=max_shape[1])
+        out[..., 1::2].clamp_(min=0, max=max_shape[0])
+    return out
+
+
+class RoIStage:
+    """``bbox_heads[i](roi_feats [K,C,7,7]) -> (cls_score [K,num_classes+1], bbox_pred [K,4])`` (class-agnostic
+    regression, as every NuHTC config sets); ``mask_head(roi_feats [D,C,14,14], det_index [D]) -> logits [D,1,h,w]``;
+    ``score_fn(cls_score) -> scores`` (softmax for stock HTC; the Seesaw activation for NuHTC)."""
+
+    def __init__(self, cfg: RoIStageConfig, bbox_heads: Sequence[Callable], mask_head: Callable,
+                 score_fn: Optional[Callable] = None):
+        assert len(bbox_heads) == cfg.num_stages
+        self.cfg = cfg
+        self.bbox_heads = list(bbox_heads)
+        self.mask_head = mask_head
+        self.score_fn = score_fn or (lambda s: torch.softmax(s, dim=-1))
+        self.timer: Optional[Callable] = None   # optional: timer(name) -> context manager (bench.py uses CUDA events)
+        self.trace: Optional[dict] = None       # optional: filled with the tensors at every op boundary (parity tests)
+
+    def _t(self, name: str):
+        return self.timer(name) if self.timer is not None else contextlib.nullcontext()
+
+    def _rec(self, **kw):
+        if self.trace is not None:
+            for k, v in kw.items():
+                self.trace.setdefault(k, []).append(v)
+
+    # -- RoI extractors: one launch over all levels -------------------------------------------------------
+    def extract(self, feats: Sequence[torch.Tensor], rois: torch.Tensor, out_size: int, sampling_ratio: int) -> torch.Tensor:
+        cfg = self.cfg
+        if cfg.extractor == "single":
+            lv = list(feats[: len(cfg.featmap_strides)])
+            return roi_align_levels(lv, rois, out_size, [1.0 / s for s in cfg.featmap_strides[: len(lv)]], sampling_ratio,
+                                    True, mode="route", finest_scale=cfg.finest_scale)
+        if cfg.extractor == "sum":
+            lv = list(feats[: cfg.sum_levels])
+            return roi_align_levels(lv, rois, out_size, [1.0 / s for s in cfg.featmap_strides[: cfg.sum_levels]],
+                                    sampling_ratio, True, mode="sum")
+        raise ValueError(cfg.extractor)
+
+    # -- the stage ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run(self, feats: Sequence[torch.Tensor], rois: torch.Tensor, max_rois_per_tile: Optional[int] = None) -> RoIStageResult:
+        cfg = self.cfg
+        B = feats[0].shape[0]
+        dev = rois.device
+        K = rois.shape[0]
+        C = cfg.num_classes
+        tile_of_roi = rois[:, 0].to(torch.int32)
+        ms_scores = []
+        bbox_pred = None
+        for i in range(cfg.num_stages):
+            with self._t("roi_align_bbox"):
+                bbox_feats = self.extract(feats, rois, cfg.bbox_out, cfg.bbox_sampling_ratio)
+            self._rec(bbox_rois=rois, bbox_feats=bbox_feats)
+            cls_score, bbox_pred = self.bbox_heads[i](bbox_feats)
+            ms_scores.append(cls_score)
+            if i < cfg.num_stages - 1:
+                # regress_by_class with reg_class_agnostic=True (mmdet bbox_head.py:459-496)
+                new = delta2bbox(rois[:, 1:], bbox_pred, cfg.stage_stds[i], cfg.img_shape)
+                rois = torch.cat([rois[:, :1], new], dim=1)
+        cls_score = sum(ms_scores) / float(len(ms_scores))
+        scores = self.score_fn(cls_score)
+        bboxes = delta2bbox(rois[:, 1:], bbox_pred, cfg.stage_stds[-1], cfg.img_shape)
+        bboxes = bboxes / cfg.scale_factor  # rescale=True: detections live in the tile frame
+
+        # multiclass_nms for every tile at once (nuhtc/models/bbox_head.py:12-102): class-agnostic boxes are
+        # expanded per class, candidates at or below score_thr are parked in a negative group, the rest go
+        # through one grouped NMS launch with the per-image class offsets.
+        cand_boxes = bboxes[:, None, :].expand(K, C, 4).reshape(-1, 4)
+        cand_scores = scores[:, :C].reshape(-1)
+        cand_labels = torch.arange(C, device=dev, dtype=torch.int64).repeat(K)
+        cand_tile = tile_of_roi.repeat_interleave(C)
+        groups = torch.where(cand_scores > cfg.score_thr, cand_tile, torch.full_like(cand_tile, -1))
+        if max_rois_per_tile is None:
+            max_rois_per_tile = int(torch.bincount(tile_of_roi.long(), minlength=B).max().item())
+        with self._t("nms"):
+            keep, gstart, gcount, status = nms_groups(cand_boxes, cand_scores, cand_labels, groups, B, max_rois_per_tile * C,
+                                                      cfg.nms_iou, 0, "offset")
+        self._rec(nms_boxes=bboxes, nms_scores=scores, nms_keep=keep, nms_start=gstart, nms_count=gcount)
+        # max_per_img truncation; one small D2H of the per-tile counts sizes the mask branch
+        cnt = torch.clamp(gcount, max=cfg.max_per_img) if cfg.max_per_img > 0 else gcount
+        host = torch.stack([gstart, cnt]).cpu()
+        if int(status.item()) != 0:
+            raise RuntimeError(f"nms_groups status {int(status.item())}: a tile exceeded max_rois_per_tile*num_classes")
+        sel = torch.cat([torch.arange(s, s + c, device=dev) for s, c in zip(host[0].tolist(), host[1].tolist())]) \
+            if int(host[1].sum()) > 0 else torch.zeros(0, dtype=torch.int64, device=dev)
+        det_cand = keep[sel]
+        det_boxes = cand_boxes[det_cand].contiguous()
+        det_scores = cand_scores[det_cand].contiguous()
+        det_labels = cand_labels[det_cand]
+        det_tile = cand_tile[det_cand].contiguous()
+        D = det_boxes.shape[0]
+
+        # mask branch: RoIAlign 14x14 on the detections (network frame), mask head, paste into the tile frame
+        mask_rois = torch.cat([det_tile.to(torch.float32)[:, None], det_boxes * cfg.scale_factor], dim=1)
+        with self._t("roi_align_mask"):
+            mask_feats = self.extract(feats, mask_rois, cfg.mask_out, cfg.mask_sampling_ratio)
+        self._rec(mask_rois=mask_rois, mask_feats=mask_feats)
+        logits = self.mask_head(mask_feats, det_cand)
+        probs = logits.sigmoid()
+        H, W = cfg.ori_shape
+        if cfg.dense_masks:
+            with self._t("paste"):
+                masks, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bin", want_stats=True)
+            with self._t("pack"):
+                bits, area, bbox = pack_masks(masks)
+        else:
+            masks = None
+            with self._t("paste"):
+                bits, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bits", want_stats=True)
+        self._rec(paste_probs=probs, paste_boxes=det_boxes)
+
+        # tools/infer_wsi.py:510-521 margin / min_area filter, then per-tile mask NMS (:526)
+        ok = ((det_boxes[:, 0] >= cfg.margin) & (det_boxes[:, 1] >= cfg.margin) & (det_boxes[:, 2] <= W - cfg.margin) &
+              (det_boxes[:, 3] <= H - cfg.margin) & (area >= cfg.min_area))
+        tile_ids = torch.where(ok, det_tile, torch.full_like(det_tile, -1))
+        cap = cfg.max_per_img if cfg.max_per_img > 0 else max(D, 1)
+        with self._t("mask_nms"):
+            keep2, tstart, tcount, st2 = mask_nms_device(bits, area, bbox, det_scores, W, cfg.mask_nms_thr, tile=tile_ids,
+                                                         num_tiles=B, max_tile_size=cap)
+        self._rec(mnms_tile=tile_ids)
+        return RoIStageResult(det_boxes, det_scores, det_labels, det_tile, masks, bits, area, keep2, tstart, tcount)

@@ -1,0 +1,222 @@
+"""Multi-GPU cross-tile merge: each rank owns the nuclei of its stripe of tile rows; only the nuclei that can
+touch another stripe ("band" nuclei) travel, with one variable-length all-gather, and only their 1-byte states
+travel during the resolve.
+
+Why this is exact.  The greedy merge of tools/nuclei_merge.py:114-150 is the unique fixed point of
+    kept(b)       <=> every overlapping (IoU > thr) nucleus that outranks b is suppressed
+    suppressed(b) <=> some overlapping nucleus that outranks b is kept
+over the global score order.  A nucleus lies inside its tile, so two nuclei of different ranks can only overlap if
+each intersects the other stripe's extent -- i.e. both are band nuclei.  After the band exchange every rank
+therefore holds ALL suppressors of its own nuclei (own nuclei + halo copies of foreign band nuclei) and can build
+its part of the suppression graph locally (csrc/merge.cu, same kernels as the single-GPU merge).  The resolve rounds
+update own nuclei only; between rounds the states of the band nuclei are all-gathered so halo copies follow their
+owners.  The loop ends when no rank has an undecided own nucleus; the result equals the single-GPU merge bit for bit.
+The final ``nuclei_id`` (rank of a kept nucleus among all kept, nuclei_merge.py:201) comes from one all-gather of
+the kept (score, id) pairs.
+
+``engine`` abstracts the two device calls so that the host protocol can be exercised on CPU with gloo (tests inject an
+oracle-backed engine); the product engine is CUDA only.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+__all__ = ["CudaMergeEngine", "merge_distributed", "stripe_extent"]
+
+
+class CudaMergeEngine:
+    """nuhtc_merge_graph / nuhtc_merge_rounds of libnuhtc_b200.so."""
+
+    def graph(self, xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor, thr: float):
+        L.require_cuda(xy, "xy")
+        dev = xy.device
+        N = score.numel()
+        lib = L.lib()
+        indeg = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
+        in_off = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        cap = 8 * N + 1024
+        import ctypes
+        for _ in range(8):
+            in_list = torch.empty(cap, dtype=torch.int32, device=dev)
+            wsb = lib.nuhtc_merge_workspace_bytes(N, xy.shape[0], cap)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            npairs = ctypes.c_int64(0)
+            with torch.cuda.device(dev):
+                rc = lib.nuhtc_merge_graph(xy.data_ptr(), voff.data_ptr(), score.data_ptr(), N, xy.shape[0], float(thr), cap,
+                                           indeg.data_ptr(), in_off.data_ptr(), in_list.data_ptr(), ctypes.byref(npairs),
+                                           status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev))
+            if rc == -4:
+                cap = int(npairs.value) + 1024
+                continue
+            L.check(rc, "merge_graph")
+            L.count("merge")
+            return indeg[:N], in_off, in_list
+        raise L.NuhtcError("merge_graph: candidate-pair capacity could not be satisfied")
+
+    def rounds(self, in_off, indeg, in_list, frozen, state, nrounds: int) -> torch.Tensor:
+        dev = state.device
+        remaining = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.lib().nuhtc_merge_rounds(in_off.data_ptr(), indeg.data_ptr(), in_list.data_ptr(), state.numel(),
+                                            L.ptr(frozen), state.data_ptr(), remaining.data_ptr(), int(nrounds), L.stream_ptr(dev))
+        L.check(rc, "merge_rounds")
+        return remaining
+
+
+def stripe_extent(shard_meta: Dict, rows: Tuple[int, int]) -> Optional[Tuple[float, float]]:
+    """y-range covered by the tiles of a stripe of tile rows [r0, r1)."""
+    r0, r1 = rows
+    if r1 <= r0:
+        return None
+    return float(r0 * shard_meta["stride"]), float((r1 - 1) * shard_meta["stride"] + shard_meta["tile"])
+
+
+def _all_gather_ragged(t: torch.Tensor, counts: List[int], group) -> List[torch.Tensor]:
+    """all-gather of per-rank tensors with different leading sizes: pad to the maximum, gather, trim."""
+    mx = max(max(counts), 1)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in counts]
+    dist.all_gather(outs, pad, group=group)
+    return [o[:c] for o, c in zip(outs, counts)]
+
+
+def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor, shard: Dict, rank: int, world: int,
+                      overlap_threshold: float = 0.05, merge_strategy: str = "probability", engine=None, group=None,
+                      return_ids: bool = False):
+    """Returns this rank's kept LOCAL indices (score-descending); with ``return_ids`` also their global nuclei_id."""
+    if merge_strategy != "probability":
+        raise NotImplementedError("the multi-GPU merge implements merge_strategy='probability' (the documented default)")
+    from .slide import stripe_rows
+    engine = engine or CudaMergeEngine()
+    dev = xy.device
+    N = score.numel()
+    gid = torch.as_tensor(shard["gid"], dtype=torch.int64, device=dev)
+    cnt = voff[1:] - voff[:-1]
+    seg = torch.repeat_interleave(torch.arange(N, device=dev), cnt)
+    ymin = torch.full((N,), float("inf"), dtype=torch.float64, device=dev).scatter_reduce(0, seg, xy[:, 1], "amin")
+    ymax = torch.full((N,), float("-inf"), dtype=torch.float64, device=dev).scatter_reduce(0, seg, xy[:, 1], "amax")
+    extents = [stripe_extent(shard, stripe_rows(shard["tiles_y"], q, world)) for q in range(world)]
+
+    # ---- band = own nuclei that reach into another rank's stripe
+    band = torch.zeros(N, dtype=torch.bool, device=dev)
+    for q, e in enumerate(extents):
+        if q != rank and e is not None:
+            band |= (ymax >= e[0]) & (ymin <= e[1])
+    bidx = band.nonzero().squeeze(1)
+    nb = int(bidx.numel())
+    bcnt = cnt[bidx]
+    bvoff = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
+    bvoff[1:] = torch.cumsum(bcnt, 0)
+    nv = int(bvoff[-1].item()) if nb else 0
+    if nb:
+        bseg = torch.repeat_interleave(torch.arange(nb, device=dev), bcnt)
+        src = voff[bidx][bseg] + (torch.arange(nv, device=dev) - bvoff[:-1][bseg])
+        bxy = xy[src]
+    else:
+        bxy = xy[:0]
+    # ---- one exchange of the band nuclei (counts, then padded records)
+    sizes = torch.tensor([nb, nv], dtype=torch.int64, device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [s.tolist() for s in all_sizes]
+    ncounts = [s[0] for s in all_sizes]
+    vcounts = [s[1] for s in all_sizes]
+    meta = torch.stack([score[bidx], gid[bidx].to(torch.float64), bcnt.to(torch.float64), ymin[bidx], ymax[bidx]], dim=1) \
+        if nb else torch.zeros((0, 5), dtype=torch.float64, device=dev)
+    g_meta = _all_gather_ragged(meta, ncounts, group)
+    g_xy = _all_gather_ragged(bxy, vcounts, group)
+
+    # ---- halo = foreign band nuclei that reach into MY stripe
+    me = extents[rank]
+    h_score, h_gid, h_cnt, h_xy, h_src = [], [], [], [], []
+    for q in range(world):
+        if q == rank or ncounts[q] == 0 or me is None:
+            continue
+        m = g_meta[q]
+        take = (m[:, 4] >= me[0]) & (m[:, 3] <= me[1])
+        tidx = take.nonzero().squeeze(1)
+        if tidx.numel() == 0:
+            continue
+        c = m[:, 2].to(torch.int64)
+        off = torch.zeros(c.numel() + 1, dtype=torch.int64, device=dev)
+        off[1:] = torch.cumsum(c, 0)
+        tc = c[tidx]
+        tseg = torch.repeat_interleave(torch.arange(tidx.numel(), device=dev), tc)
+        toff = torch.zeros(tidx.numel() + 1, dtype=torch.int64, device=dev)
+        toff[1:] = torch.cumsum(tc, 0)
+        vsrc = off[:-1][tidx][tseg] + (torch.arange(int(toff[-1]), device=dev) - toff[:-1][tseg])
+        h_score.append(m[tidx, 0]); h_gid.append(m[tidx, 1].to(torch.int64)); h_cnt.append(tc); h_xy.append(g_xy[q][vsrc])
+        h_src.append(torch.stack([torch.full_like(tidx, q), tidx], dim=1))
+    H = int(sum(t.numel() for t in h_score))
+    if H:
+        a_score = torch.cat([score] + h_score)
+        a_gid = torch.cat([gid] + h_gid)
+        a_cnt = torch.cat([cnt] + h_cnt)
+        a_xy = torch.cat([xy] + h_xy)
+        halo_src = torch.cat(h_src)
+    else:
+        a_score, a_gid, a_cnt, a_xy = score, gid, cnt, xy
+        halo_src = torch.zeros((0, 2), dtype=torch.int64, device=dev)
+    M = N + H
+    # order the local set by global id so that equal scores are ranked like the single-GPU merge (lower index first)
+    perm = torch.argsort(a_gid, stable=True)
+    p_cnt = a_cnt[perm]
+    p_voff = torch.zeros(M + 1, dtype=torch.int64, device=dev)
+    p_voff[1:] = torch.cumsum(p_cnt, 0)
+    a_voff = torch.zeros(M + 1, dtype=torch.int64, device=dev)
+    a_voff[1:] = torch.cumsum(a_cnt, 0)
+    pseg = torch.repeat_interleave(torch.arange(M, device=dev), p_cnt)
+    psrc = a_voff[:-1][perm][pseg] + (torch.arange(int(p_voff[-1]), device=dev) - p_voff[:-1][pseg])
+    p_xy = a_xy[psrc].contiguous()
+    p_score = a_score[perm].contiguous()
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(M, device=dev)          # position of local-set element i in the permuted arrays
+
+    indeg, in_off, in_list = engine.graph(p_xy, p_voff, p_score, overlap_threshold)
+    frozen = torch.zeros(M, dtype=torch.uint8, device=dev)
+    frozen[inv[N:]] = 1
+    state = torch.where((indeg[:M] == 0) & (frozen == 0), 1, 0).to(torch.uint8)
+    own_pos = inv[:N]
+    band_pos = own_pos[bidx]
+    halo_pos = inv[N:]
+
+    # ---- resolve: exchange band states, sweep own nuclei, until nobody has an undecided own nucleus
+    for _ in range(1 << 20):
+        g_state = _all_gather_ragged(state[band_pos], ncounts, group)
+        if H:
+            flat_off = [0]
+            for c in ncounts:
+                flat_off.append(flat_off[-1] + c)
+            flat = torch.cat(g_state)
+            state[halo_pos] = flat[torch.as_tensor(flat_off[:-1], device=dev)[halo_src[:, 0]] + halo_src[:, 1]]
+        remaining = engine.rounds(in_off, indeg, in_list, frozen, state, 4)
+        tot = remaining.clone()
+        dist.all_reduce(tot, group=group)
+        if int(tot.item()) == 0:
+            break
+    kept_local = (state[own_pos] == 1).nonzero().squeeze(1)
+    order = torch.argsort(-score[kept_local], stable=True)
+    kept_local = kept_local[order]
+    if not return_ids:
+        return kept_local
+    # ---- global nuclei_id = rank among all kept nuclei (score desc, then id)
+    kc = torch.tensor([int(kept_local.numel())], dtype=torch.int64, device=dev)
+    all_kc = [torch.empty_like(kc) for _ in range(world)]
+    dist.all_gather(all_kc, kc, group=group)
+    all_kc = [int(k.item()) for k in all_kc]
+    rec = torch.stack([score[kept_local], gid[kept_local].to(torch.float64)], dim=1)
+    g_rec = torch.cat(_all_gather_ragged(rec, all_kc, group))
+    o1 = torch.argsort(g_rec[:, 1], stable=True)
+    o2 = torch.argsort(-g_rec[o1, 0], stable=True)
+    glob_order = o1[o2]                                  # positions sorted by (score desc, id asc)
+    pos = torch.empty_like(glob_order)
+    pos[glob_order] = torch.arange(glob_order.numel(), device=dev)
+    start = sum(all_kc[:rank])
+    return kept_local, pos[start: start + all_kc[rank]]

@@ -35,7 +35,7 @@ def proposals(B: int, n_per: int, dist: str = "nuclei", frame: int = 512, seed: 
     return torch.cat([bidx, x1y1, x2y2], dim=1)
 
 
-def nms_boxes(N: int, num_classes: int = 5, seed: int = 0, density: float = 3.0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def nms_boxes(N: int, num_classes: int = 5, seed: int = 0, density: float = 30.0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Boxes w,h~U(8,32) with centres uniform over a square sized so that on average `density` same-class boxes
     cover a point (keep ratio ~30-60% at IoU 0.5); scores are a random permutation of a linspace (distinct)."""
     g = torch.Generator().manual_seed(seed + 31)
@@ -130,3 +130,33 @@ def slide_nuclei(tiles_x: int, tiles_y: int, per_tile: int = 23, tile: int = 256
     score = rng.permutation(np.linspace(0.36, 0.999, N))
     return dict(xy=xy, voff=voff, score=score.astype(np.float64), tile_id=tid.astype(np.int64), tiles_x=tiles_x,
                 tiles_y=tiles_y, stride=stride, tile=tile)
+
+
+class SyntheticHeads:
+    """Stand-ins for the bbox / mask heads (stock cuDNN modules, outside this package's target): their outputs are
+    seeded tensors that do not depend on the pooled features, so the RoI-stage ops see realistic shapes and value
+    ranges (class logits, small box deltas, blob-shaped mask logits) without any convolution in the timed region."""
+
+    def __init__(self, K: int, num_classes: int = 5, num_stages: int = 3, pool: int = 509, mask_size: int = 28, seed: int = 0,
+                 device="cpu"):
+        g = torch.Generator().manual_seed(seed + 211)
+        self.cls = [(torch.randn(K, num_classes + 1, generator=g) * 1.5).to(device) for _ in range(num_stages)]
+        self.reg = [(torch.randn(K, 4, generator=g) * 0.5).to(device) for _ in range(num_stages)]
+        u = (torch.arange(mask_size, dtype=torch.float32) + 0.5) / mask_size * 2 - 1
+        a = 0.55 + 0.4 * torch.rand(pool, 1, 1, generator=g)
+        b = 0.55 + 0.4 * torch.rand(pool, 1, 1, generator=g)
+        r2 = (u[None, :, None] / b) ** 2 + (u[None, None, :] / a) ** 2
+        self.pool = (6.0 * (1.0 - r2))[:, None].contiguous().to(device)   # logits; sigmoid > 0.5 inside the ellipse
+        self.pool_n = pool
+
+    def bbox_heads(self):
+        return [(lambda feats, i=i: (self.cls[i], self.reg[i])) for i in range(len(self.cls))]
+
+    def mask_head(self, feats, det_cand):
+        return self.pool[det_cand % self.pool_n]
+
+    def to(self, device):
+        self.cls = [t.to(device) for t in self.cls]
+        self.reg = [t.to(device) for t in self.reg]
+        self.pool = self.pool.to(device)
+        return self

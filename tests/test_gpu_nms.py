@@ -68,7 +68,7 @@ def test_offset_arithmetic_is_reproduced(oracle):
     """Large coordinates: the fp32 class offset perturbs the IoUs; keep must still be identical."""
     import nuhtc_b200 as nb
     from nuhtc_b200 import synth
-    boxes, scores, labels = synth.nms_boxes(8000, seed=5, density=6.0)
+    boxes, scores, labels = synth.nms_boxes(8000, seed=5, density=40.0)
     boxes = boxes + 3000.0
     cfg = dict(type="nms", iou_threshold=0.5)
     _, k_ref = oracle.batched_nms(boxes, scores, labels, cfg)
