@@ -17,6 +17,8 @@
 //    column, which is what lets the kernel run at the HBM write rate instead of the L1 rate.
 //  * roi_align_direct_kernel -- literal per-sample restatement (any layout / shape), same float op
 //    order as the CPU reference; used as fallback and as an on-device cross-check.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 struct RoiLevels {
@@ -159,8 +161,7 @@ __global__ void __launch_bounds__(256) roi_align_direct_kernel(RoiLevels lv, int
 // ---------------------------------------------------------------------------------------------
 // separable fast kernel (NHWC input)
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxTap = 8;   // taps per bin per axis held in the tables
-constexpr int kMaxRows = 48; // window rows per RoI handled by the fast path
+constexpr int kMaxTap = 8; // taps per bin per axis held in the tables; larger bins take the literal path
 
 template <int P>
 struct SepCfg {
@@ -169,9 +170,10 @@ struct SepCfg {
     static constexpr int S = (PP % 8 == 1) ? PP : (PP + ((9 - PP % 8) % 8));
 };
 
-// per-axis tap table for bin p: accumulated bilinear weights over the g samples of the bin
-__device__ __forceinline__ bool build_axis_taps(float start, float bin, int g, int p, int D, float *w, int &first,
-                                                int &n) {
+// per-axis tap table for bin p: accumulated bilinear weights over the g samples of the bin, each
+// divided by `div` (1 for x, the sample count for y).  n = -1 flags a bin with more than kMaxTap taps.
+__device__ __forceinline__ void build_axis_taps(float start, float bin, int g, int p, int D, float div, float *w, int *first,
+                                                int *n) {
 #pragma unroll
     for (int j = 0; j < kMaxTap; ++j) w[j] = 0.f;
     int base = -1, last = -1;
@@ -191,33 +193,108 @@ __device__ __forceinline__ bool build_axis_taps(float start, float bin, int g, i
         w[b] += l;
         last = b;
     }
-    first = base < 0 ? 0 : base;
-    n = last + 1;
-    return ok;
+    if (ok && div != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < kMaxTap; ++j) w[j] = __fdiv_rn(w[j], div);
+    }
+    *first = base < 0 ? 0 : base;
+    *n = ok ? last + 1 : -1;
 }
 
-// PHS: the P output rows are split over PHS thread groups (keeps the accumulators at P/PHS float4)
-template <int P, int NQ, int PHS>
-__global__ void __launch_bounds__(NQ *P *PHS) roi_align_sep_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int sr,
-                                                              int aligned, int mode, float finest,
-                                                              float *__restrict__ out) {
-    constexpr int CC = NQ * 4;
+// two fp32 FMAs in one instruction (Blackwell FFMA2): d = a * {b.x, b.y} + c
+__device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
+// One sweep over the window rows [y0, y1) for a thread that owns output column pw (NX x-taps starting at
+// the pointer) and PB output rows: t = sum_j wx[j] * V[y][xs+j] per row, then acc[i] += wy[i][y-ys[i]] * t.
+template <int NX, int PB, int VEC, int QSTRIDE>
+__device__ __forceinline__ void sweep_rows(const float *__restrict__ rowp, size_t rstride, int C, int y0, int y1,
+                                           const float *__restrict__ s_wxp, const float *__restrict__ s_wyp, const int (&ys)[PB],
+                                           const int (&ny)[PB], float2 (&acc)[PB][VEC][2], int nx_rt = 0) {
+    constexpr int NXR = NX > 0 ? NX : 1;
+    float wx[NXR];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) wx[j] = s_wxp[j];
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y, rowp += rstride) {
+        float2 t[VEC][2];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            t[u][0] = make_float2(0.f, 0.f);
+            t[u][1] = make_float2(0.f, 0.f);
+        }
+        if (NX > 0) {
+            // all NX*VEC gathers are issued before the first FMA consumes one
+            float4 v[NXR][VEC];
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) v[j][u] = ldg_f4(rowp + (size_t)j * C + u * QSTRIDE);
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) {
+                    t[u][0] = ffma2(wx[j], make_float2(v[j][u].x, v[j][u].y), t[u][0]);
+                    t[u][1] = ffma2(wx[j], make_float2(v[j][u].z, v[j][u].w), t[u][1]);
+                }
+        } else {
+            // wide bins (5..kMaxTap taps): runtime tap count, weights from shared memory
+#pragma unroll 2
+            for (int j = 0; j < nx_rt; ++j) {
+                const float w = s_wxp[j];
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) {
+                    const float4 vv = ldg_f4(rowp + (size_t)j * C + u * QSTRIDE);
+                    t[u][0] = ffma2(w, make_float2(vv.x, vv.y), t[u][0]);
+                    t[u][1] = ffma2(w, make_float2(vv.z, vv.w), t[u][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+            const int jj = y - ys[i];
+            if ((unsigned)jj < (unsigned)ny[i]) {
+                const float w = s_wyp[i * kMaxTap + jj];
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) {
+                    acc[i][u][0] = ffma2(w, t[u][0], acc[i][u][0]);
+                    acc[i][u][1] = ffma2(w, t[u][1], acc[i][u][1]);
+                }
+            }
+        }
+    }
+}
+
+// P output size; NQ channel quads per VEC slice; PHS: the P output rows are split over PHS thread groups;
+// VEC: float4 slices per thread (a thread owns channels 4q..4q+3 of each slice).  CTA = (RoI, CC channels).
+template <int P, int NQ, int PHS, int VEC, int MINB>
+__global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int sr,
+                                                                    int aligned, int mode, float finest,
+                                                                    float *__restrict__ out) {
+    constexpr int CC = NQ * 4 * VEC;
     constexpr int PP = SepCfg<P>::PP;
     constexpr int S = SepCfg<P>::S;
     constexpr int NT = NQ * P * PHS;
     constexpr int PB = P / PHS;
     static_assert(P % PHS == 0, "row split must divide P");
+    static_assert(NT >= 32 + P, "tap builders sit on warps 0 and 1");
     extern __shared__ __align__(16) float smem[];
-    float *s_tile = smem;                    // [CC][S]
-    float *s_wx = s_tile + CC * S;           // [P][kMaxTap]
-    float *s_wy = s_wx + P * kMaxTap;        // [P][kMaxTap]
-    float *s_wyd = s_wy + P * kMaxTap;       // [P][kMaxRows] dense, already divided by count
-    int *s_xs = (int *)(s_wyd + P * kMaxRows); // [P] first tap column
+    float *s_tile = smem;                // [CC][S]
+    float *s_wx = s_tile + CC * S;       // [P][kMaxTap]
+    float *s_wy = s_wx + P * kMaxTap;    // [P][kMaxTap], already divided by the sample count
+    int *s_xs = (int *)(s_wy + P * kMaxTap);
     int *s_nx = s_xs + P;
     int *s_ys = s_nx + P;
     int *s_ny = s_ys + P;
-    int *s_ok = s_ny + P;            // [2P]
-    int *s_rowmask = s_ok + 2 * P;   // [kMaxRows]
+    int *s_meta = s_ny + P;              // [0] level, [1] batch index
 
     const int k = blockIdx.x;
     const int c0 = blockIdx.y * CC;
@@ -227,119 +304,72 @@ __global__ void __launch_bounds__(NQ *P *PHS) roi_align_sep_kernel(RoiLevels lv,
     const int ph0 = (tid / (NQ * P)) * PB; // first output row owned by this thread
     const float *roi = rois + (size_t)k * 5;
 
-    float4 acc[PB];
+    float2 acc[PB][VEC][2];
 #pragma unroll
-    for (int i = 0; i < PB; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < PB; ++i)
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) acc[i][u][0] = acc[i][u][1] = make_float2(0.f, 0.f);
 
-    int l0 = 0, l1 = lv.L;
-    if (mode == NUHTC_ROI_ROUTE) {
-        l0 = route_level(roi, lv.L, finest);
-        l1 = l0 + 1;
-    }
-    for (int l = l0; l < l1; ++l) {
-        const int H = lv.H[l], W = lv.W[l];
-        const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
-        if (l != l0) __syncthreads(); // previous level's tables are still being read
-        // ---- phase A: tap tables (x bins on warp 0, y bins on warp 1)
-        if (tid < P) {
-            int f, n;
-            const bool ok = build_axis_taps(g.start_w, g.bin_w, g.gw, tid, W, s_wx + tid * kMaxTap, f, n);
-            s_xs[tid] = f;
-            s_nx[tid] = n;
-            s_ok[tid] = ok;
-        } else if (tid >= 32 && tid < 32 + P) {
-            const int p = tid - 32;
-            int f, n;
-            const bool ok = build_axis_taps(g.start_h, g.bin_h, g.gh, p, H, s_wy + p * kMaxTap, f, n);
-            s_ys[p] = f;
-            s_ny[p] = n;
-            s_ok[P + p] = ok;
-        }
-        __syncthreads();
-        bool fast = true;
-        int ymin = 1 << 30, ymax = -1;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            fast = fast && s_ok[p] && s_ok[P + p];
-            const int n = s_ny[p];
-            if (n > 0) {
-                ymin = min(ymin, s_ys[p]);
-                ymax = max(ymax, s_ys[p] + n);
+    const int nlev = mode == NUHTC_ROI_ROUTE ? 1 : lv.L;
+    for (int it = 0; it < nlev; ++it) {
+        if (it) __syncthreads(); // the previous level's tables are still being read
+        // ---- phase A: the RoI geometry and the tap tables are computed by 2P threads only (x bins on warp 0,
+        // y bins on warp 1); everybody else waits at the barrier instead of redoing the divisions
+        const bool xb = tid < P, yb = tid >= 32 && tid < 32 + P;
+        if (xb || yb) {
+            const int l = mode == NUHTC_ROI_ROUTE ? route_level(roi, lv.L, finest) : it;
+            const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+            if (xb) {
+                build_axis_taps(g.start_w, g.bin_w, g.gw, tid, lv.W[l], 1.0f, s_wx + tid * kMaxTap, s_xs + tid, s_nx + tid);
+                if (tid == 0) {
+                    s_meta[0] = l;
+                    s_meta[1] = g.b;
+                }
+            } else {
+                const int p = tid - 32;
+                build_axis_taps(g.start_h, g.bin_h, g.gh, p, lv.H[l], g.count, s_wy + p * kMaxTap, s_ys + p, s_ny + p);
             }
         }
-        const int nrows = ymax - ymin; // <= 0 when no valid row
-        fast = fast && nrows <= kMaxRows;
-        if (fast) {
-            if (nrows > 0) {
-                // ---- phase B: dense row weights and the row -> bins mask
-                for (int i = tid; i < P * kMaxRows; i += NT) {
-                    const int p = i / kMaxRows, r = i - p * kMaxRows;
-                    const int j = r + ymin - s_ys[p];
-                    float w = 0.f;
-                    if (r < nrows && j >= 0 && j < s_ny[p]) w = __fdiv_rn(s_wy[p * kMaxTap + j], g.count);
-                    s_wyd[i] = w;
-                }
-                if (tid < kMaxRows) {
-                    int m = 0;
+        __syncthreads();
+        const int l = s_meta[0], b = s_meta[1];
+        const int H = lv.H[l], W = lv.W[l];
+        const int nx = s_nx[pw];
+        int ys[PB], ny[PB];
+        bool slow = nx < 0;
+        int y0 = 1 << 30, y1 = -1;
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const int j = tid + ymin - s_ys[p];
-                        if (tid < nrows && j >= 0 && j < s_ny[p]) m |= 1 << p;
-                    }
-                    s_rowmask[tid] = m;
-                }
-                __syncthreads();
-                // ---- phase C: one sweep over the window rows
-                float wx[kMaxTap];
-                const int nx = s_nx[pw];
-#pragma unroll
-                for (int j = 0; j < kMaxTap; ++j) wx[j] = s_wx[pw * kMaxTap + j];
-                // rows touched by this thread's own output rows
-                int r0 = nrows, r1 = 0;
-#pragma unroll
-                for (int i = 0; i < PB; ++i) {
-                    const int n = s_ny[ph0 + i];
-                    if (n > 0) {
-                        r0 = min(r0, s_ys[ph0 + i] - ymin);
-                        r1 = max(r1, s_ys[ph0 + i] + n - ymin);
-                    }
-                }
-                const float *rowp =
-                    lv.data[l] + (((size_t)g.b * H + ymin + r0) * W + s_xs[pw]) * (size_t)C + c0 + 4 * q;
+        for (int i = 0; i < PB; ++i) {
+            ys[i] = s_ys[ph0 + i];
+            ny[i] = s_ny[ph0 + i];
+            slow = slow || ny[i] < 0;
+            if (ny[i] > 0) {
+                y0 = min(y0, ys[i]);
+                y1 = max(y1, ys[i] + ny[i]);
+            }
+        }
+        const float *img = lv.data[l] + (size_t)b * H * W * C + c0 + 4 * q;
+        if (!slow) {
+            if (nx > 0 && y1 > y0) {
+                const float *rowp = img + ((size_t)y0 * W + s_xs[pw]) * (size_t)C;
                 const size_t rstride = (size_t)W * C;
-#pragma unroll 2
-                for (int r = r0; r < r1; ++r, rowp += rstride) {
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int j = 0; j < kMaxTap; ++j) {
-                        if (j < nx) {
-                            const float4 v = ldg_f4(rowp + (size_t)j * C);
-                            t.x = fmaf(wx[j], v.x, t.x);
-                            t.y = fmaf(wx[j], v.y, t.y);
-                            t.z = fmaf(wx[j], v.z, t.z);
-                            t.w = fmaf(wx[j], v.w, t.w);
-                        }
-                    }
-                    const int m = s_rowmask[r] >> ph0;
-#pragma unroll
-                    for (int i = 0; i < PB; ++i) {
-                        if ((m >> i) & 1) {
-                            const float w = s_wyd[(ph0 + i) * kMaxRows + r];
-                            acc[i].x = fmaf(w, t.x, acc[i].x);
-                            acc[i].y = fmaf(w, t.y, acc[i].y);
-                            acc[i].z = fmaf(w, t.z, acc[i].z);
-                            acc[i].w = fmaf(w, t.w, acc[i].w);
-                        }
-                    }
+                const float *wxp = s_wx + pw * kMaxTap, *wyp = s_wy + ph0 * kMaxTap;
+                switch (nx) {
+                    case 1: sweep_rows<1, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    case 2: sweep_rows<2, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    case 3: sweep_rows<3, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    case 4: sweep_rows<4, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    default: sweep_rows<0, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc, nx); break;
                 }
             }
         } else {
-            // ---- oversized RoI: literal per-sample accumulation, same thread mapping
-            const float *img = lv.data[l] + (size_t)g.b * H * W * C + c0 + 4 * q;
+            // ---- a bin of this thread is wider than the tap table (very large RoI): literal per-sample path
+            const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
 #pragma unroll 1
             for (int pi = 0; pi < PB; ++pi) {
                 const int ph = ph0 + pi;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                float a[VEC][4];
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) a[u][0] = a[u][1] = a[u][2] = a[u][3] = 0.f;
                 for (int iy = 0; iy < g.gh; ++iy) {
                     int yl, yh;
                     float ly, hy;
@@ -349,30 +379,37 @@ __global__ void __launch_bounds__(NQ *P *PHS) roi_align_sep_kernel(RoiLevels lv,
                         float lx, hx;
                         const bool okx = axis_sample(sample_coord(g.start_w, g.bin_w, pw, ix, g.gw), W, xl, xh, lx, hx);
                         if (!(oky && okx)) continue;
-                        const float4 v1 = ldg_f4(img + ((size_t)yl * W + xl) * C), v2 = ldg_f4(img + ((size_t)yl * W + xh) * C);
-                        const float4 v3 = ldg_f4(img + ((size_t)yh * W + xl) * C), v4 = ldg_f4(img + ((size_t)yh * W + xh) * C);
                         const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-                        a.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-                        a.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-                        a.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-                        a.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) {
+                            const float *pu = img + u * NQ * 4;
+                            const float4 v1 = ldg_f4(pu + ((size_t)yl * W + xl) * C), v2 = ldg_f4(pu + ((size_t)yl * W + xh) * C);
+                            const float4 v3 = ldg_f4(pu + ((size_t)yh * W + xl) * C), v4 = ldg_f4(pu + ((size_t)yh * W + xh) * C);
+                            a[u][0] += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+                            a[u][1] += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+                            a[u][2] += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+                            a[u][3] += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+                        }
                     }
                 }
-                // acc is indexed statically below: fold this bin into the matching register
+                // acc is indexed statically: fold this bin into the matching registers
 #pragma unroll
                 for (int pp = 0; pp < PB; ++pp) {
                     if (pp == pi) {
-                        acc[pp].x += __fdiv_rn(a.x, g.count);
-                        acc[pp].y += __fdiv_rn(a.y, g.count);
-                        acc[pp].z += __fdiv_rn(a.z, g.count);
-                        acc[pp].w += __fdiv_rn(a.w, g.count);
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) {
+                            acc[pp][u][0].x += __fdiv_rn(a[u][0], g.count);
+                            acc[pp][u][0].y += __fdiv_rn(a[u][1], g.count);
+                            acc[pp][u][1].x += __fdiv_rn(a[u][2], g.count);
+                            acc[pp][u][1].y += __fdiv_rn(a[u][3], g.count);
+                        }
                     }
                 }
             }
         }
     }
 
-    // ---- transpose [4 ch of this thread][ph][pw] into the [CC][S] staging tile.
+    // ---- transpose [channels of this thread][ph][pw] into the [CC][S] staging tile.
     // Lanes of a warp hold consecutive channel quads (stride 4*S words == 4 mod 32), so the four
     // channels are written in a lane-rotated order that spreads the 32 lanes over all 32 banks.
     const int lane = tid & 31;
@@ -380,10 +417,14 @@ __global__ void __launch_bounds__(NQ *P *PHS) roi_align_sep_kernel(RoiLevels lv,
 #pragma unroll
     for (int i = 0; i < PB; ++i) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int j = (jj + rot) & 3;
-            const float v = j == 0 ? acc[i].x : (j == 1 ? acc[i].y : (j == 2 ? acc[i].z : acc[i].w));
-            s_tile[(4 * q + j) * S + (ph0 + i) * P + pw] = v;
+        for (int u = 0; u < VEC; ++u) {
+            const float a0 = acc[i][u][0].x, a1 = acc[i][u][0].y, a2 = acc[i][u][1].x, a3 = acc[i][u][1].y;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = (jj + rot) & 3;
+                const float v = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
+                s_tile[(u * NQ * 4 + 4 * q + j) * S + (ph0 + i) * P + pw] = v;
+            }
         }
     }
     __syncthreads();
@@ -410,24 +451,34 @@ __global__ void __launch_bounds__(NQ *P *PHS) roi_align_sep_kernel(RoiLevels lv,
     }
 }
 
-template <int P, int NQ>
+template <int P, int NQ, int VEC>
 static size_t sep_smem_bytes() {
-    return sizeof(float) * (NQ * 4 * SepCfg<P>::S + 2 * P * kMaxTap + P * kMaxRows) + sizeof(int) * (6 * P + kMaxRows);
+    return sizeof(float) * (NQ * 4 * VEC * SepCfg<P>::S + 2 * P * kMaxTap) + sizeof(int) * (4 * P + 4);
 }
 
-template <int P, int NQ, int PHS>
+template <int P, int NQ, int PHS, int VEC, int MINB>
 static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
                       float *out, cudaStream_t st) {
     static bool attr_done = false;
-    const size_t smem = sep_smem_bytes<P, NQ>();
+    const size_t smem = sep_smem_bytes<P, NQ, VEC>();
     if (!attr_done) {
-        NUHTC_CUDA(cudaFuncSetAttribute(roi_align_sep_kernel<P, NQ, PHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NUHTC_CUDA(cudaFuncSetAttribute(roi_align_sep_kernel<P, NQ, PHS, VEC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid(K, C / (NQ * 4));
-    roi_align_sep_kernel<P, NQ, PHS><<<grid, NQ * P * PHS, smem, st>>>(lv, C, rois, sr, aligned, mode, finest, out);
+    dim3 grid(K, C / (NQ * 4 * VEC));
+    roi_align_sep_kernel<P, NQ, PHS, VEC, MINB><<<grid, NQ * P * PHS, smem, st>>>(lv, C, rois, sr, aligned, mode, finest, out);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
+}
+
+// tuning knob (A/B on the GPU box): NUHTC_RA_VEC=1 keeps one float4 slice per thread
+static int ra_vec() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NUHTC_RA_VEC");
+        v = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2; // 1: one slice/thread; 2: two slices, 2 CTAs/SM; 3: two slices, 3 CTAs/SM
+    }
+    return v;
 }
 
 NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const int *W, const float *scale, int L, int B,
@@ -457,12 +508,22 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
     const bool fast_ok = impl == NUHTC_IMPL_AUTO && layout == NUHTC_LAYOUT_NHWC && PH == PW && (PH == 7 || PH == 14) &&
                          C % 64 == 0 && aligned16;
     if (fast_ok) {
+        const int sr = sampling_ratio;
+        const bool v2 = ra_vec() >= 2;
         if (PH == 7) {
-            if (C % 256 == 0) return launch_sep<7, 64, 1>(lv, C, rois, K, sampling_ratio, aligned, mode, finest_scale, out, st);
-            if (C % 128 == 0) return launch_sep<7, 32, 1>(lv, C, rois, K, sampling_ratio, aligned, mode, finest_scale, out, st);
-            return launch_sep<7, 16, 1>(lv, C, rois, K, sampling_ratio, aligned, mode, finest_scale, out, st);
+            if (C % 256 == 0) {
+                if (ra_vec() == 3) return launch_sep<7, 32, 1, 2, 3>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+                if (v2) return launch_sep<7, 32, 1, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+                return launch_sep<7, 64, 1, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            }
+            if (C % 128 == 0) {
+                if (v2) return launch_sep<7, 16, 1, 2, 4>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+                return launch_sep<7, 32, 1, 1, 4>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            }
+            return launch_sep<7, 16, 1, 1, 8>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
         }
-        return launch_sep<14, 16, 2>(lv, C, rois, K, sampling_ratio, aligned, mode, finest_scale, out, st);
+        if (v2) return launch_sep<14, 8, 2, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+        return launch_sep<14, 16, 2, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
     }
     const long total = (long)K * C * PH * PW;
     const int threads = 256;
@@ -474,6 +535,7 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // NCHW -> NHWC (once per level per batch; HBM-bound transpose through a padded smem tile)
