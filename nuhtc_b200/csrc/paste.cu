@@ -6,15 +6,21 @@
 // without materialising the [N,H,W,2] sampling grid or the fp32 [N,H,W] intermediate: the
 // normalised coordinate of every output pixel is recomputed from the box in the reference's own
 // float op order, and ATen's grid_sampler_2d (bilinear, zeros padding, align_corners=False) is
-// applied in registers.  One CTA owns one mask: the [mh,mw] probability map is staged in shared
-// memory only if the box touches the image; every thread then produces 16 output pixels per step
-// and leaves through a 128-bit streaming store.  Outside the box's reach the result is exactly
-// zero (zeros padding), so most of the kernel is a store stream -- HBM-write bound.
+// applied in registers.
+//
+// The dense output contract ([N,H,W] per mask) makes this a store stream: a nucleus covers ~1 % of its
+// 256x256 frame and everything outside the box's reach is exactly zero (zeros padding).  So the work is
+// split in two launches on the same stream:
+//   fill   : a grid-stride 128-bit streaming zero fill of the whole output (HBM-write bound, no per-mask
+//            prologue on its critical path)
+//   sparse : one CTA per mask evaluates only the 16-pixel segments (64-pixel words for bit rows) that the
+//            box can reach, staged probability map in shared memory, and overwrites them; it also
+//            reduces the per-mask area and tight bounding box that the mask NMS consumes.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kPasteThreads = 256;
+constexpr int kPasteThreads = 128;
 constexpr int kMaxMaskElems = 64 * 64; // staged probability map (28x28 in every NuHTC config)
 
 // normalised grid coordinate of pixel centre p+0.5 for a box side [a0,a1] (fcn_mask_head.py:388-400)
@@ -29,7 +35,7 @@ __device__ __forceinline__ float unnormalize(float g, int size) {
 }
 
 struct AxisTap {
-    int i0;      // floor index; i0+1 is the other tap
+    int i0;       // floor index; i0+1 is the other tap
     float w0, w1; // weights of i0 and i0+1
 };
 __device__ __forceinline__ AxisTap axis_tap(int p, float a0, float a1, int size) {
@@ -68,10 +74,26 @@ __device__ __forceinline__ void active_range(float a0, float a1, int size, int e
     hi = h < 0.f ? 0 : (h > (float)extent ? extent : (int)h);
 }
 
+// ---- launch 1: zero fill (n16 16-byte chunks + a byte tail), grid-stride, 4 stores in flight per thread
+__global__ void __launch_bounds__(256) fill_zero_kernel(uint4 *__restrict__ p, size_t n16, uint8_t *__restrict__ tail, int ntail) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        st_stream_u4(p + i, z);
+        st_stream_u4(p + i + stride, z);
+        st_stream_u4(p + i + 2 * stride, z);
+        st_stream_u4(p + i + 3 * stride, z);
+    }
+    for (; i < n16; i += stride) st_stream_u4(p + i, z);
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+
+// ---- launch 2: the reachable region of every mask
 template <int KIND>
-__global__ void __launch_bounds__(kPasteThreads) paste_kernel(const float *__restrict__ probs, const float *__restrict__ boxes,
-                                                              int mh, int mw, int H, int W, float thr, void *__restrict__ outv,
-                                                              int32_t *__restrict__ area, int32_t *__restrict__ bbox) {
+__global__ void __launch_bounds__(kPasteThreads) paste_sparse_kernel(const float *__restrict__ probs, const float *__restrict__ boxes,
+                                                                     int mh, int mw, int H, int W, float thr, void *__restrict__ outv,
+                                                                     int32_t *__restrict__ area, int32_t *__restrict__ bbox) {
     __shared__ float s_m[kMaxMaskElems];
     __shared__ int s_red[5][kPasteThreads / 32];
     const int n = blockIdx.x, tid = threadIdx.x;
@@ -79,66 +101,73 @@ __global__ void __launch_bounds__(kPasteThreads) paste_kernel(const float *__res
     int ax0, ax1, ay0, ay1;
     active_range(bx0, bx1, mw, W, ax0, ax1);
     active_range(by0, by1, mh, H, ay0, ay1);
-    if (!(thr > 0.f)) { // 0 >= thr holds for the zero padding too: every pixel must be evaluated
+    if (KIND != NUHTC_PASTE_PROB && !(thr > 0.f)) { // 0 >= thr holds for the zero padding too: evaluate every pixel
         ax0 = ay0 = 0;
         ax1 = W;
         ay1 = H;
     }
     const bool any = ax1 > ax0 && ay1 > ay0;
-    if (any) {
+    int cnt = 0, minx = 1 << 30, miny = 1 << 30, maxx = -1, maxy = -1;
+    if (any) { // uniform over the CTA
         const float *src = probs + (size_t)n * mh * mw;
         for (int i = tid; i < mh * mw; i += kPasteThreads) s_m[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    int cnt = 0, minx = 1 << 30, miny = 1 << 30, maxx = -1, maxy = -1;
-
-    if (KIND == NUHTC_PASTE_BITS) {
-        const int wpr = (W + 63) / 64;
-        unsigned long long *out = (unsigned long long *)outv + (size_t)n * H * wpr;
-        for (int i = tid; i < H * wpr; i += kPasteThreads) {
-            const int y = i / wpr, xw = (i - y * wpr) * 64;
-            unsigned long long word = 0ull;
-            if (any && y >= ay0 && y < ay1 && xw < ax1 && xw + 64 > ax0) {
-                const AxisTap ty = axis_tap(y, by0, by1, mh);
-                const int xa = max(xw, ax0), xb = min(min(xw + 64, ax1), W);
-                for (int x = xa; x < xb; ++x) {
-                    const float v = sample(s_m, mh, mw, ty, axis_tap(x, bx0, bx1, mw));
-                    if (v >= thr) {
-                        word |= 1ull << (x - xw);
-                        minx = min(minx, x);
-                        maxx = max(maxx, x);
-                    }
-                }
-                if (word) {
-                    cnt += __popcll(word);
-                    miny = min(miny, y);
-                    maxy = max(maxy, y);
-                }
-            }
-            out[i] = word;
-        }
-    } else {
-        // 16 pixels (KIND BIN: 16 bytes) or 4 pixels (KIND PROB: 16 bytes) per thread per step
-        constexpr int PX = KIND == NUHTC_PASTE_BIN ? 16 : 4;
-        const size_t total = (size_t)H * W;
-        char *outb = (char *)outv + (size_t)n * total * (KIND == NUHTC_PASTE_BIN ? 1 : 4);
-        const bool vec_ok = (W % PX == 0) && (((uintptr_t)outb) % 16 == 0);
-        if (vec_ok) {
-            const int segs_per_row = W / PX;
-            for (int i = tid; i < H * segs_per_row; i += kPasteThreads) {
-                const int y = i / segs_per_row, xs = (i - y * segs_per_row) * PX;
-                float v[PX];
-#pragma unroll
-                for (int u = 0; u < PX; ++u) v[u] = 0.f;
-                const bool live = any && y >= ay0 && y < ay1 && xs < ax1 && xs + PX > ax0;
+        __syncthreads();
+        const int nrows = ay1 - ay0;
+        if (KIND == NUHTC_PASTE_BITS) {
+            const int wpr = (W + 63) / 64;
+            unsigned long long *out = (unsigned long long *)outv + (size_t)n * H * wpr;
+            const int w0 = ax0 >> 6, nw = ((ax1 + 63) >> 6) - w0;
+            // 4 lanes share one 64-pixel word (16 pixels each) so that a nucleus keeps a whole CTA busy
+            const int sub = tid & 3;
+            const int ntask = nrows * nw;
+            for (int base = 0; base < ntask; base += kPasteThreads / 4) { // trip count uniform over the CTA (shuffles below)
+                const int i = base + (tid >> 2);
+                const bool live = i < ntask;
+                const int y = ay0 + (live ? i / nw : 0), xw = (w0 + (live ? i % nw : 0)) * 64;
+                unsigned long long part = 0ull;
                 if (live) {
                     const AxisTap ty = axis_tap(y, by0, by1, mh);
+#pragma unroll 4
+                    for (int u = 0; u < 16; ++u) {
+                        const int x = xw + sub * 16 + u;
+                        if (x >= ax0 && x < ax1 && x < W) {
+                            const float v = sample(s_m, mh, mw, ty, axis_tap(x, bx0, bx1, mw));
+                            if (v >= thr) {
+                                part |= 1ull << (sub * 16 + u);
+                                minx = min(minx, x);
+                                maxx = max(maxx, x);
+                            }
+                        }
+                    }
+                }
+                part |= __shfl_xor_sync(0xffffffffu, part, 1);
+                part |= __shfl_xor_sync(0xffffffffu, part, 2);
+                if (live && sub == 0) {
+                    out[(size_t)y * wpr + (xw >> 6)] = part;
+                    if (part) {
+                        cnt += __popcll(part);
+                        miny = min(miny, y);
+                        maxy = max(maxy, y);
+                    }
+                }
+            }
+        } else {
+            // 16 pixels (BIN: 16 bytes) or 4 pixels (PROB: 16 bytes) per thread per step
+            constexpr int PX = KIND == NUHTC_PASTE_BIN ? 16 : 4;
+            const size_t total = (size_t)H * W;
+            char *outb = (char *)outv + (size_t)n * total * (KIND == NUHTC_PASTE_BIN ? 1 : 4);
+            const bool vec_ok = (W % PX == 0) && (((uintptr_t)outb) % 16 == 0);
+            if (vec_ok) {
+                const int s0 = ax0 / PX, ns = (ax1 + PX - 1) / PX - s0;
+                for (int i = tid; i < nrows * ns; i += kPasteThreads) {
+                    const int y = ay0 + i / ns, xs = (s0 + i % ns) * PX;
+                    const AxisTap ty = axis_tap(y, by0, by1, mh);
+                    float v[PX];
 #pragma unroll
                     for (int u = 0; u < PX; ++u) v[u] = sample(s_m, mh, mw, ty, axis_tap(xs + u, bx0, bx1, mw));
-                }
-                if (KIND == NUHTC_PASTE_BIN) {
-                    uint32_t w[4] = {0u, 0u, 0u, 0u};
-                    if (live) {
+                    const size_t seg = ((size_t)y * W + xs) / PX;
+                    if (KIND == NUHTC_PASTE_BIN) {
+                        uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                         for (int u = 0; u < PX; ++u) {
                             if (v[u] >= thr) {
@@ -150,30 +179,29 @@ __global__ void __launch_bounds__(kPasteThreads) paste_kernel(const float *__res
                                 maxy = max(maxy, y);
                             }
                         }
+                        st_stream_u4(outb + seg * 16, make_uint4(w[0], w[1], w[2], w[3]));
+                    } else {
+                        st_stream_f4((float *)outb + seg * 4, make_float4(v[0], v[1], v[2], v[3]));
                     }
-                    st_stream_u4(outb + (size_t)i * 16, make_uint4(w[0], w[1], w[2], w[3]));
-                } else {
-                    st_stream_f4((float *)outb + (size_t)i * 4, make_float4(v[0], v[1], v[2], v[3]));
                 }
-            }
-        } else {
-            for (size_t i = tid; i < total; i += kPasteThreads) {
-                const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
-                float v = 0.f;
-                if (any && y >= ay0 && y < ay1 && x >= ax0 && x < ax1)
-                    v = sample(s_m, mh, mw, axis_tap(y, by0, by1, mh), axis_tap(x, bx0, bx1, mw));
-                if (KIND == NUHTC_PASTE_BIN) {
-                    const bool on = any && v >= thr && y >= ay0 && y < ay1 && x >= ax0 && x < ax1;
-                    ((uint8_t *)outb)[i] = on ? 1 : 0;
-                    if (on) {
-                        ++cnt;
-                        minx = min(minx, x);
-                        maxx = max(maxx, x);
-                        miny = min(miny, y);
-                        maxy = max(maxy, y);
+            } else {
+                const int nc = ax1 - ax0;
+                for (int i = tid; i < nrows * nc; i += kPasteThreads) {
+                    const int y = ay0 + i / nc, x = ax0 + i % nc;
+                    const float v = sample(s_m, mh, mw, axis_tap(y, by0, by1, mh), axis_tap(x, bx0, bx1, mw));
+                    if (KIND == NUHTC_PASTE_BIN) {
+                        const bool on = v >= thr;
+                        ((uint8_t *)outb)[(size_t)y * W + x] = on ? 1 : 0;
+                        if (on) {
+                            ++cnt;
+                            minx = min(minx, x);
+                            maxx = max(maxx, x);
+                            miny = min(miny, y);
+                            maxy = max(maxy, y);
+                        }
+                    } else {
+                        ((float *)outb)[(size_t)y * W + x] = v;
                     }
-                } else {
-                    ((float *)outb)[i] = v;
                 }
             }
         }
@@ -223,16 +251,27 @@ NUHTC_API int nuhtc_paste_masks(const float *probs, const float *boxes, int N, i
     NUHTC_CHECK_ARG(out_kind >= NUHTC_PASTE_PROB && out_kind <= NUHTC_PASTE_BITS, "paste: bad out_kind %d", out_kind);
     if (N == 0) return NUHTC_OK;
     NUHTC_CHECK_ARG(probs && boxes && out, "paste: null pointer");
+    NUHTC_CHECK_ARG(((uintptr_t)out) % 16 == 0, "paste: output must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes;
+    if (out_kind == NUHTC_PASTE_PROB) bytes = (size_t)N * img_h * img_w * 4;
+    else if (out_kind == NUHTC_PASTE_BIN) bytes = (size_t)N * img_h * img_w;
+    else bytes = (size_t)N * img_h * ((img_w + 63) / 64) * 8;
+    const size_t n16 = bytes / 16;
+    const int ntail = (int)(bytes % 16);
+    size_t want = (n16 + 4 * 256 - 1) / (4 * 256);
+    const size_t cap = (size_t)nuhtc_sm_count() * 8; // a multiple of the SM count, 8 resident CTAs each
+    const unsigned fgrid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+    fill_zero_kernel<<<fgrid, 256, 0, st>>>((uint4 *)out, n16, (uint8_t *)out + n16 * 16, ntail);
     switch (out_kind) {
         case NUHTC_PASTE_PROB:
-            paste_kernel<NUHTC_PASTE_PROB><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
+            paste_sparse_kernel<NUHTC_PASTE_PROB><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
             break;
         case NUHTC_PASTE_BIN:
-            paste_kernel<NUHTC_PASTE_BIN><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
+            paste_sparse_kernel<NUHTC_PASTE_BIN><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
             break;
         default:
-            paste_kernel<NUHTC_PASTE_BITS><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
+            paste_sparse_kernel<NUHTC_PASTE_BITS><<<N, kPasteThreads, 0, st>>>(probs, boxes, mh, mw, img_h, img_w, thr, out, area, bbox);
     }
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
