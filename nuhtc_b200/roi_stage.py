@@ -18,7 +18,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
-from .mask_nms import mask_nms_device, pack_masks
+from .mask_nms import mask_nms_device
 from .mask_paste import paste_masks
 from .mmcv_ops import nms_groups, roi_align_levels
 
@@ -198,15 +198,15 @@ class RoIStage:
         logits = self.mask_head(mask_feats, det_cand)
         probs = logits.sigmoid()
         H, W = cfg.ori_shape
+        # the bit rows (+ area / tight box) feed the mask NMS; the dense uint8 frames are what get_seg_masks returns.
+        # Both come straight from the 28x28 maps: re-reading 64 KB per nucleus to pack it would cost more than
+        # evaluating its ~1e3 reachable pixels twice.
+        with self._t("paste_bits"):
+            bits, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bits", want_stats=True)
+        masks = None
         if cfg.dense_masks:
             with self._t("paste"):
-                masks, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bin", want_stats=True)
-            with self._t("pack"):
-                bits, area, bbox = pack_masks(masks)
-        else:
-            masks = None
-            with self._t("paste"):
-                bits, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bits", want_stats=True)
+                masks = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bin")
         self._rec(paste_probs=probs, paste_boxes=det_boxes)
 
         # tools/infer_wsi.py:510-521 margin / min_area filter, then per-tile mask NMS (:526)
