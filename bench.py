@@ -45,7 +45,7 @@ def parse():
     p.add_argument("--proposals", type=int, default=1000)
     p.add_argument("--channels", type=int, default=256)
     p.add_argument("--max-per-img", type=int, default=500)
-    p.add_argument("--dist", default="routed", choices=["nuclei", "routed"], help="proposal size distribution")
+    p.add_argument("--dist", default="nuclei", choices=["nuclei", "routed"], help="proposal size distribution")
     p.add_argument("--lane", default="dense", choices=["dense", "bits"], help="paste output: dense uint8 masks or bit rows")
     p.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     p.add_argument("--cpu-tiles", type=int, default=2, help="tiles in the bounded CPU-baseline sample")

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
     constexpr int PB = P / PHS;
     static_assert(P % PHS == 0, "row split must divide P");
     static_assert(NT >= 32 + P, "tap builders sit on warps 0 and 1");
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float *s_tile = smem;                // [CC][S]
     float *s_wx = s_tile + CC * S;       // [P][kMaxTap]
     float *s_wy = s_wx + P * kMaxTap;    // [P][kMaxTap], already divided by the sample count
@@ -471,6 +471,463 @@ static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int 
     return NUHTC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// pipelined fast kernel: persistent CTAs, one producer warp + NQ*P*PHS consumer threads
+// ---------------------------------------------------------------------------------------------
+// The v2 kernel above exposes one L2 round trip per window row to every consumer warp.  Here a producer
+// warp runs ahead of the consumers: for every work item (RoI, channel chunk, level) it builds the tap
+// tables into a double-buffered slot and streams the window rows [y0,y1) x [x0,x0+ww) of the NHWC level
+// into a shared-memory ring with TMA bulk copies (cp.async.bulk, completion on an mbarrier).  The consumer
+// warps wait on the row's "full" barrier, take their taps with conflict-free LDS.128, and release the
+// row to the producer through its "empty" barrier.  Window rows wider than the ring stage, or bins with
+// more than kMaxTap taps, fall back to the direct global-load sweep of the v2 kernel inside the same CTA.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+constexpr int kPipeMaxRows = 40; // staged windows taller than this take the direct path
+
+template <int P>
+struct PipeSlot { // tap tables + geometry of one work item
+    float wx[P][kMaxTap];
+    float wy[P][kMaxTap]; // already divided by the sample count
+    int xs[P], nx[P], ys[P], ny[P];
+    int mode;   // 0 staged rows, 1 direct global sweep, 2 literal (a bin exceeds the tap table)
+    int x0, ww; // staged column range
+    int y0, y1; // window rows
+    int level, batch, k, c0, last, pad0, pad1;
+    // dense y weights of the staged rows: wyd[y - y0][bin] (0 where the bin does not touch the row), 8 floats per
+    // group of up to 7 bins so that a consumer takes its weights of a row with two LDS.128 and no compares
+    float wyd[kPipeMaxRows][(P + 6) / 7 * 8];
+};
+
+enum { kPipeStaged = 0, kPipeDirect = 1, kPipeLiteral = 2 };
+constexpr int kPipeSlots = 4;
+
+__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// position in the row ring: stage index and the parity of its current use
+struct RingPos {
+    unsigned stage, parity;
+    template <int NS>
+    __device__ __forceinline__ void next() {
+        if (++stage == NS) {
+            stage = 0;
+            parity ^= 1u;
+        }
+    }
+};
+
+// consumer: staged rows for a thread with NX x-taps (NX == 0: runtime count, weights from the slot) and PB (<= 7)
+// output rows whose dense weights sit at wyd[row][0..7]
+template <int NX, int PB, int NS, int WYS>
+__device__ __forceinline__ void staged_rows(const float *ring, int stage_floats, int CC, int y0, int y1, int xoff, int q,
+                                            const float *s_wxp, const float *s_wyd, float2 (&acc)[PB][1][2], uint32_t full0,
+                                            uint32_t empty0, RingPos &rp, int nx_rt, int my0, int my1) {
+    constexpr int NXR = NX > 0 ? NX : 1;
+    float wx[NXR];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) wx[j] = s_wxp[j];
+    const int lane = threadIdx.x & 31;
+    for (int y = y0; y < y1; ++y, s_wyd += WYS) {
+        mbar_wait(full0 + 8 * rp.stage, rp.parity);
+        if (y >= my0 && y < my1) {
+            const float *row = ring + (size_t)rp.stage * stage_floats + (size_t)xoff * CC + 4 * q;
+            float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+            if (NX > 0) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {
+                    const float4 v = *reinterpret_cast<const float4 *>(row + (size_t)j * CC);
+                    t0 = ffma2(wx[j], make_float2(v.x, v.y), t0);
+                    t1 = ffma2(wx[j], make_float2(v.z, v.w), t1);
+                }
+            } else {
+                for (int j = 0; j < nx_rt; ++j) {
+                    const float4 v = *reinterpret_cast<const float4 *>(row + (size_t)j * CC);
+                    const float w = s_wxp[j];
+                    t0 = ffma2(w, make_float2(v.x, v.y), t0);
+                    t1 = ffma2(w, make_float2(v.z, v.w), t1);
+                }
+            }
+            const float4 wa = *reinterpret_cast<const float4 *>(s_wyd), wb = *reinterpret_cast<const float4 *>(s_wyd + 4);
+            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                acc[i][0][0] = ffma2(w[i], t0, acc[i][0][0]);
+                acc[i][0][1] = ffma2(w[i], t1, acc[i][0][1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
+        rp.next<NS>();
+    }
+}
+
+// Warp roles: [0, NCONS) consumers, warp NCONS/32 builds tap tables (kPipeSlots items ahead), warp NCONS/32+1 streams rows.
+template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
+__global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
+    roi_align_pipe_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int K, int sr, int aligned, int mode, float finest,
+                          float *__restrict__ out) {
+    constexpr int CC = NQ * 4;
+    constexpr int PP = SepCfg<P>::PP;
+    constexpr bool kBulkStore = SepCfg<P>::S == PP;            // contiguous tile == contiguous global chunk
+    constexpr int S = SepCfg<P>::S;
+    constexpr int NWORK = NQ * P * PHS;              // consumer threads that own outputs
+    constexpr int NCONS = (NWORK + 31) / 32 * 32;    // padded to whole warps: the tail threads only keep the barriers company
+    constexpr int CONS_WARPS = NCONS / 32;
+    constexpr int PB = P / PHS;
+    constexpr int STAGE_FLOATS = WMAX * CC;
+    static_assert(P <= 16, "x bins on lanes 0..15, y bins on lanes 16..31 of the tap warp");
+    extern __shared__ __align__(128) float smem[];
+    float *s_ring = smem;                                   // [NS][WMAX][CC]
+    float *s_tile = s_ring + (size_t)NS * STAGE_FLOATS;     // [CC][S]
+    PipeSlot<P> *s_slot = reinterpret_cast<PipeSlot<P> *>(s_tile + CC * S); // [kPipeSlots]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_slot + kPipeSlots);    // full[NS], empty[NS], tfull[slots], tempty[slots]
+    const uint32_t full0 = smem_u32(s_bar), empty0 = full0 + 8 * NS, tfull0 = empty0 + 8 * NS, tempty0 = tfull0 + 8 * kPipeSlots;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, CONS_WARPS);
+        }
+        for (int s = 0; s < kPipeSlots; ++s) {
+            mbar_init(tfull0 + 8 * s, 32);
+            mbar_init(tempty0 + 8 * s, CONS_WARPS + 1); // every consumer warp + the copy warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nchunk = C / CC;
+    const int nlev = mode == NUHTC_ROI_ROUTE ? 1 : lv.L;
+    const long nunits = (long)K * nchunk; // a unit = (RoI, channel chunk); its levels are consecutive items
+    unsigned itemctr = 0;
+    constexpr int WYS = (P + 6) / 7 * 8;
+    static_assert(PB <= 7, "a consumer owns at most 7 output rows");
+
+    if (tid >= NCONS + 32) {
+        // =========================== copy warp: streams the window rows of every staged item ===========================
+        const int lane = tid - NCONS - 32;
+        RingPos rp{0u, 0u};
+        for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+            for (int it = 0; it < nlev; ++it, ++itemctr) {
+                const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
+                mbar_wait(tfull0 + 8 * slot, use & 1);
+                const PipeSlot<P> &sl = s_slot[slot];
+                const int md = sl.mode, x0 = sl.x0, ww = sl.ww, y0 = sl.y0, y1 = sl.y1, l = sl.level, b = sl.batch, c0 = sl.c0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * slot); // the slot's geometry is in registers now
+                if (md == kPipeStaged && y1 > y0) {
+                    const int H = lv.H[l], W = lv.W[l];
+                    const float *src0 = lv.data[l] + (((size_t)b * H + y0) * W + x0) * (size_t)C + c0;
+                    const size_t rstride = (size_t)W * C;
+                    for (int y = y0; y < y1; ++y, rp.next<NS>()) {
+                        const unsigned stage = rp.stage;
+                        mbar_wait(empty0 + 8 * stage, rp.parity ^ 1u);
+                        const uint32_t dst = smem_u32(s_ring + (size_t)stage * STAGE_FLOATS);
+                        const float *src = src0 + (size_t)(y - y0) * rstride;
+                        if (nchunk == 1) { // the row segment is contiguous in NHWC
+                            if (lane == 0) {
+                                mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)ww * CC * 4);
+                                tma_bulk_g2s(dst, src, (uint32_t)ww * CC * 4, full0 + 8 * stage);
+                            }
+                        } else {           // one CC-channel piece per pixel
+                            if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)ww * CC * 4);
+                            for (int x = lane; x < ww; x += 32)
+                                tma_bulk_g2s(dst + (uint32_t)x * CC * 4, src + (size_t)x * C, CC * 4, full0 + 8 * stage);
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+    if (tid >= NCONS) {
+        // =========================== tap warp: tables + window geometry, kPipeSlots items ahead ===========================
+        const int lane = tid - NCONS;
+        for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+            const int chunk = (int)(unit % nchunk);
+            const int k = (int)(unit / nchunk);
+            const float *roi = rois + (size_t)k * 5;
+            for (int it = 0; it < nlev; ++it, ++itemctr) {
+                const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
+                mbar_wait(tempty0 + 8 * slot, (use & 1) ^ 1);
+                PipeSlot<P> &sl = s_slot[slot];
+                const int l = mode == NUHTC_ROI_ROUTE ? route_level(roi, lv.L, finest) : it;
+                const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+                const int H = lv.H[l], W = lv.W[l];
+                int first = 0, n = 0;
+                if (lane < P) {
+                    build_axis_taps(g.start_w, g.bin_w, g.gw, lane, W, 1.0f, sl.wx[lane], &first, &n);
+                    sl.xs[lane] = first;
+                    sl.nx[lane] = n;
+                } else if (lane >= 16 && lane < 16 + P) {
+                    build_axis_taps(g.start_h, g.bin_h, g.gh, lane - 16, H, g.count, sl.wy[lane - 16], &first, &n);
+                    sl.ys[lane - 16] = first;
+                    sl.ny[lane - 16] = n;
+                }
+                // window = union of the bins' tap ranges: reductions over the x half (lanes 0..15) and the y half (16..31)
+                const bool has = ((lane < P) || (lane >= 16 && lane < 16 + P)) && n > 0;
+                const bool bad = ((lane < P) || (lane >= 16 && lane < 16 + P)) && n < 0;
+                int lo = has ? first : (1 << 30), hi = has ? first + n : -1;
+#pragma unroll
+                for (int o = 8; o; o >>= 1) {
+                    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                }
+                const int x0 = __shfl_sync(0xffffffffu, lo, 0), x1 = __shfl_sync(0xffffffffu, hi, 0);
+                const int y0 = __shfl_sync(0xffffffffu, lo, 16), y1 = __shfl_sync(0xffffffffu, hi, 16);
+                const bool lit = __any_sync(0xffffffffu, bad);
+                const bool empty = x1 <= x0 || y1 <= y0;
+                const int ww = empty ? 0 : x1 - x0;
+                const bool staged = !lit && ww <= WMAX && (empty || y1 - y0 <= kPipeMaxRows);
+                if (staged && !empty) {
+                    // dense y weights: lane r owns window rows r, r+32
+                    __syncwarp(); // the bin lanes' wy / ys / ny are in the slot
+                    for (int r = lane; r < y1 - y0; r += 32) {
+                        float w[WYS];
+#pragma unroll
+                        for (int i = 0; i < WYS; ++i) w[i] = 0.f;
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const int jj = y0 + r - sl.ys[p];
+                            if ((unsigned)jj < (unsigned)sl.ny[p]) w[p / 7 * 8 + p % 7] = sl.wy[p][jj];
+                        }
+#pragma unroll
+                        for (int i = 0; i < WYS; i += 4)
+                            *reinterpret_cast<float4 *>(&sl.wyd[r][i]) = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+                    }
+                }
+                if (lane == 0) {
+                    sl.mode = lit ? kPipeLiteral : (staged ? kPipeStaged : kPipeDirect);
+                    sl.x0 = empty ? 0 : x0;
+                    sl.ww = ww;
+                    sl.y0 = empty ? 0 : y0;
+                    sl.y1 = empty ? 0 : y1;
+                    sl.level = l;
+                    sl.batch = g.b;
+                    sl.k = k;
+                    sl.c0 = chunk * CC;
+                    sl.last = it == nlev - 1;
+                }
+                mbar_arrive(tfull0 + 8 * slot); // all 32 lanes arrive: each releases its own table writes
+            }
+        }
+        return;
+    }
+
+    // =========================== consumer warps ===========================
+    const bool worker = tid < NWORK;
+    const int wt = worker ? tid : 0;
+    const int q = wt % NQ;
+    const int pw = (wt / NQ) % P;
+    const int ph0 = (wt / (NQ * P)) * PB;
+    const int lane = tid & 31;
+    float2 acc[PB][1][2];
+#pragma unroll
+    for (int i = 0; i < PB; ++i) acc[i][0][0] = acc[i][0][1] = make_float2(0.f, 0.f);
+    RingPos rp{0u, 0u};
+    // flush constants of this thread: the lane-rotated channel order and the tile offsets that go with it
+    const int rot = (lane >> 3) - (lane / NQ);
+    const bool rot1 = (rot & 1) != 0, rot2 = (rot & 2) != 0;
+    int toff[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) toff[jj] = (4 * q + ((jj + rot) & 3)) * S + ph0 * P + pw;
+    for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        int k = 0, c0 = 0;
+        for (int it = 0; it < nlev; ++it, ++itemctr) {
+            const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
+            mbar_wait(tfull0 + 8 * slot, use & 1);
+            const PipeSlot<P> &sl = s_slot[slot];
+            const int md = sl.mode, y0 = sl.y0, y1 = sl.y1, l = sl.level;
+            k = sl.k;
+            c0 = sl.c0;
+            const int nx = sl.nx[pw];
+            int ys[PB], ny[PB];
+            int my0 = 1 << 30, my1 = -1;
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                ys[i] = sl.ys[ph0 + i];
+                ny[i] = sl.ny[ph0 + i];
+                if (ny[i] > 0) {
+                    my0 = min(my0, ys[i]);
+                    my1 = max(my1, ys[i] + ny[i]);
+                }
+            }
+            const float *wxp = sl.wx[pw], *wyp = sl.wy[ph0];
+            if (!worker) { my0 = 0; my1 = 0; }
+            if (md == kPipeStaged) {
+                if (y1 > y0) {
+                    const int xoff = sl.xs[pw] - sl.x0;
+                    if (nx <= 0) { my0 = 0; my1 = 0; } // no valid sample in this column: still take part in the row barriers
+                    const float *wyd = &sl.wyd[0][ph0 / 7 * 8];
+                    switch (nx) {
+                        case 1: staged_rows<1, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                        case 2: staged_rows<2, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                        case 3: staged_rows<3, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                        case 4: staged_rows<4, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                        default: staged_rows<0, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx > 0 ? nx : 0, my0, my1); break;
+                    }
+                }
+            } else if (worker) {
+                const int H = lv.H[l], W = lv.W[l];
+                const float *img = lv.data[l] + (size_t)sl.batch * H * W * C + c0 + 4 * q;
+                if (md == kPipeDirect) {
+                    if (nx > 0 && my1 > my0) {
+                        const float *rowp = img + ((size_t)my0 * W + sl.xs[pw]) * (size_t)C;
+                        sweep_rows<0, PB, 1, NQ * 4>(rowp, (size_t)W * C, C, my0, my1, wxp, wyp, ys, ny, acc, nx);
+                    }
+                } else {
+                    const float *roi = rois + (size_t)k * 5;
+                    const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+#pragma unroll 1
+                    for (int pi = 0; pi < PB; ++pi) {
+                        const int ph = ph0 + pi;
+                        float a[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int iy = 0; iy < g.gh; ++iy) {
+                            int yl, yh;
+                            float ly, hy;
+                            const bool oky = axis_sample(sample_coord(g.start_h, g.bin_h, ph, iy, g.gh), H, yl, yh, ly, hy);
+                            for (int ix = 0; ix < g.gw; ++ix) {
+                                int xl, xh;
+                                float lx, hx;
+                                const bool okx = axis_sample(sample_coord(g.start_w, g.bin_w, pw, ix, g.gw), W, xl, xh, lx, hx);
+                                if (!(oky && okx)) continue;
+                                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                                const float4 v1 = ldg_f4(img + ((size_t)yl * W + xl) * C), v2 = ldg_f4(img + ((size_t)yl * W + xh) * C);
+                                const float4 v3 = ldg_f4(img + ((size_t)yh * W + xl) * C), v4 = ldg_f4(img + ((size_t)yh * W + xh) * C);
+                                a[0] += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+                                a[1] += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+                                a[2] += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+                                a[3] += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+                            }
+                        }
+#pragma unroll
+                        for (int pp = 0; pp < PB; ++pp) {
+                            if (pp == pi) {
+                                acc[pp][0][0].x += __fdiv_rn(a[0], g.count);
+                                acc[pp][0][0].y += __fdiv_rn(a[1], g.count);
+                                acc[pp][0][1].x += __fdiv_rn(a[2], g.count);
+                                acc[pp][0][1].y += __fdiv_rn(a[3], g.count);
+                            }
+                        }
+                    }
+                }
+            }
+            // the slot can be rebuilt as soon as every consumer warp has its taps out of it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
+        }
+
+        // ---- flush the unit: transpose into the tile (lane-rotated channel order: conflict-free), stream it out
+        asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); // the previous flush has left the tile (thread 0 waited on its store)
+        if (worker) {
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                const float a0 = acc[i][0][0].x, a1 = acc[i][0][0].y, a2 = acc[i][0][1].x, a3 = acc[i][0][1].y;
+                // rotate (a0..a3) left by rot with two conditional stages (the predicates are per-thread constants)
+                const float b0 = rot2 ? a2 : a0, b1 = rot2 ? a3 : a1, b2 = rot2 ? a0 : a2, b3 = rot2 ? a1 : a3;
+                s_tile[toff[0] + i * P] = rot1 ? b1 : b0;
+                s_tile[toff[1] + i * P] = rot1 ? b2 : b1;
+                s_tile[toff[2] + i * P] = rot1 ? b3 : b2;
+                s_tile[toff[3] + i * P] = rot1 ? b0 : b3;
+                acc[i][0][0] = acc[i][0][1] = make_float2(0.f, 0.f);
+            }
+        }
+        float *outp = out + ((size_t)k * C + c0) * PP;
+        if (kBulkStore) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // my tile writes become visible to the TMA engine
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
+            if (tid == 0) {
+                tma_bulk_s2g(outp, smem_u32(s_tile), CC * PP * 4);
+                tma_store_wait_read(); // only this thread waits; the others are already on the next unit's rows
+            }
+        } else {
+            asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
+            constexpr int N4 = CC * PP / 4;
+            for (int i = tid; i < N4; i += NCONS) {
+                int c = (4 * i) / PP, e = 4 * i - c * PP;
+                float t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    t[u] = s_tile[c * S + e];
+                    if (++e == PP) {
+                        e = 0;
+                        ++c;
+                    }
+                }
+                st_stream_f4(outp + 4 * i, make_float4(t[0], t[1], t[2], t[3]));
+            }
+        }
+    }
+    if (kBulkStore && tid == 0) tma_store_wait_all(); // global writes complete before the CTA retires
+}
+
+template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
+static int launch_pipe(const RoiLevels &lv, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
+                       float *out, cudaStream_t st) {
+    static int grid_cached = 0;
+    const size_t smem = sizeof(float) * ((size_t)NS * WMAX * NQ * 4 + NQ * 4 * SepCfg<P>::S) + kPipeSlots * sizeof(PipeSlot<P>) +
+                        sizeof(uint64_t) * (2 * NS + 2 * kPipeSlots) + 128;
+    auto kern = roi_align_pipe_kernel<P, NQ, PHS, NS, WMAX, MINB>;
+    constexpr int nthreads = (NQ * P * PHS + 31) / 32 * 32 + 64;
+    if (!grid_cached) {
+        NUHTC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        NUHTC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
+        if (per_sm < 1) {
+            nuhtc_set_error("roi_align pipe kernel does not fit on an SM (smem %zu)", smem);
+            return NUHTC_ECUDA;
+        }
+        grid_cached = per_sm * nuhtc_sm_count(); // persistent: every CTA resident, a multiple of the SM count
+    }
+    const long nunits = (long)K * (C / (NQ * 4));
+    const int grid = (int)(nunits < grid_cached ? nunits : grid_cached);
+    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out);
+    NUHTC_LAUNCH_CHECK();
+    return NUHTC_OK;
+}
+
+static int ra_pipe() { // NUHTC_RA_PIPE=0 selects the v2 (non-pipelined) kernel for A/B runs
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NUHTC_RA_PIPE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 // tuning knob (A/B on the GPU box): NUHTC_RA_VEC=1 keeps one float4 slice per thread
 static int ra_vec() {
     static int v = -1;
@@ -507,6 +964,16 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
     aligned16 = aligned16 && (((uintptr_t)out) % 16 == 0);
     const bool fast_ok = impl == NUHTC_IMPL_AUTO && layout == NUHTC_LAYOUT_NHWC && PH == PW && (PH == 7 || PH == 14) &&
                          C % 64 == 0 && aligned16;
+    if (fast_ok && ra_pipe()) {
+        const int sr = sampling_ratio;
+        if (PH == 7) {
+            if (C == 256) return launch_pipe<7, 64, 1, 9, 18, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            if (C == 128) return launch_pipe<7, 32, 1, 8, 24, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            if (C == 64) return launch_pipe<7, 16, 1, 8, 24, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+        } else {
+            return launch_pipe<14, 16, 2, 8, 24, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+        }
+    }
     if (fast_ok) {
         const int sr = sampling_ratio;
         const bool v2 = ra_vec() >= 2;
