@@ -967,10 +967,14 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
     if (fast_ok && ra_pipe()) {
         const int sr = sampling_ratio;
         if (PH == 7) {
-            if (C == 256) return launch_pipe<7, 64, 1, 9, 18, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            if (C == 256) {
+                static const int narrow = getenv("NUHTC_RA_NARROW") ? atoi(getenv("NUHTC_RA_NARROW")) : 0;
+                if (!narrow) return launch_pipe<7, 64, 1, 5, 32, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+                return launch_pipe<7, 64, 1, 9, 18, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            }
             if (C == 128) return launch_pipe<7, 32, 1, 8, 24, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
             if (C == 64) return launch_pipe<7, 16, 1, 8, 24, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-        } else {
+        } else if (C == 64) { // one bulk copy per window row needs the CTA to own every channel of the level
             return launch_pipe<14, 16, 2, 8, 24, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
         }
     }
