@@ -1,0 +1,40 @@
+"""Rebind the reference's op surface to the B200 ops.  Needs mmcv / mmdet / nuhtc importable,
+i.e. it runs inside the reference's environment; nothing else in this package depends on them."""
+from __future__ import annotations
+
+import importlib
+
+
+def patch_mmcv(verbose: bool = False):
+    """``mmcv.ops.RoIAlign / roi_align / nms / batched_nms`` and the names the reference modules bound at import time
+    (`batched_nms` in four modules, `_do_paste_mask` in fcn_mask_head) now point at nuhtc_b200.  Returns the list of
+    rebound attributes."""
+    from . import RoIAlign, _do_paste_mask, batched_nms, nms, roi_align
+    import mmcv.ops
+    import mmcv.ops.nms as mmcv_nms
+
+    done = []
+
+    def bind(mod, name, obj):
+        setattr(mod, name, obj)
+        done.append(f"{mod.__name__}.{name}")
+
+    bind(mmcv.ops, "RoIAlign", RoIAlign)
+    bind(mmcv.ops, "roi_align", roi_align)
+    bind(mmcv.ops, "nms", nms)
+    bind(mmcv.ops, "batched_nms", batched_nms)
+    bind(mmcv_nms, "nms", nms)
+    bind(mmcv_nms, "batched_nms", batched_nms)
+    for modname in ("nuhtc.models.bbox_head", "nuhtc.core.post_processing.bbox_nms", "mmdet.core.post_processing.bbox_nms",
+                    "mmdet.models.dense_heads.rpn_head"):
+        try:
+            bind(importlib.import_module(modname), "batched_nms", batched_nms)
+        except ImportError:
+            pass
+    try:
+        bind(importlib.import_module("mmdet.models.roi_heads.mask_heads.fcn_mask_head"), "_do_paste_mask", _do_paste_mask)
+    except ImportError:
+        pass
+    if verbose:
+        print("nuhtc_b200.patch_mmcv:", ", ".join(done))
+    return done
