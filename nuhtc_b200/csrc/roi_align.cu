@@ -597,10 +597,10 @@ __device__ __forceinline__ void staged_rows(const float *ring, int stage_floats,
 template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
 __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
     roi_align_pipe_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int K, int sr, int aligned, int mode, float finest,
-                          float *__restrict__ out) {
+                          float *__restrict__ out, int bulk_store_flag) {
     constexpr int CC = NQ * 4;
     constexpr int PP = SepCfg<P>::PP;
-    constexpr bool kBulkStore = SepCfg<P>::S == PP;            // contiguous tile == contiguous global chunk
+    const bool kBulkStore = (SepCfg<P>::S == PP) && bulk_store_flag != 0;            // contiguous tile == contiguous global chunk
     constexpr int S = SepCfg<P>::S;
     constexpr int NWORK = NQ * P * PHS;              // consumer threads that own outputs
     constexpr int NCONS = (NWORK + 31) / 32 * 32;    // padded to whole warps: the tail threads only keep the barriers company
@@ -914,7 +914,8 @@ static int launch_pipe(const RoiLevels &lv, int C, const float *rois, int K, int
     }
     const long nunits = (long)K * (C / (NQ * 4));
     const int grid = (int)(nunits < grid_cached ? nunits : grid_cached);
-    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out);
+    static const int bulk = getenv("NUHTC_RA_BULK") ? atoi(getenv("NUHTC_RA_BULK")) : 1;
+    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out, bulk);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }

@@ -63,10 +63,35 @@ class RoIStageResult:
     keep: torch.Tensor           # [D] int32: per tile, kept detection indices (into D) in score order
     tile_start: torch.Tensor     # [B] int32
     tile_count: torch.Tensor     # [B] int32
+    det_valid: Optional[torch.Tensor] = None   # [D] bool: D = B*max_per_img slots, tile-major; invalid slots are padding
+    det_cand: Optional[torch.Tensor] = None    # [D] int64 candidate id (roi*num_classes + label) of each slot
+    status: Optional[tuple] = None             # device status words of the NMS / mask-NMS launches
+
+    def check(self) -> None:
+        """Host-side check of the device status words (one small D2H)."""
+        if self.status is not None:
+            for name, st in zip(("nms", "mask_nms"), self.status):
+                v = int(st.item())
+                if v != 0:
+                    raise RuntimeError(f"{name} status {v}: a tile exceeded its declared capacity")
 
     def kept_indices(self) -> List[torch.Tensor]:
         ts, tc = self.tile_start.cpu().tolist(), self.tile_count.cpu().tolist()
         return [self.keep[s:s + c].long() for s, c in zip(ts, tc)]
+
+    def compact(self) -> "RoIStageResult":
+        """Drop the padding slots (synchronises): detections tile-major in score order, `keep` re-indexed."""
+        self.check()
+        if self.det_valid is None or bool(self.det_valid.all()):
+            return self
+        v = self.det_valid
+        new_index = torch.cumsum(v.to(torch.int64), 0) - 1
+        nk = int(self.tile_count.sum().item())
+        keep = self.keep.clone()
+        keep[:nk] = new_index[self.keep[:nk].long()].to(self.keep.dtype)
+        return RoIStageResult(self.det_boxes[v], self.det_scores[v], self.det_labels[v], self.det_tile[v],
+                              None if self.masks is None else self.masks[v], self.mask_bits[v], self.mask_area[v], keep,
+                              self.tile_start, self.tile_count, det_valid=None, det_cand=self.det_cand[v], status=None)
 
 
 def bbox2roi(bbox_list: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -85,7 +110,9 @@ def delta2bbox(rois: torch.Tensor, deltas: torch.Tensor, stds, max_shape=None, m
     """Class-agnostic form of mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:163-260 (same op order)."""
     if deltas.size(0) == 0:
         return deltas
-    d = deltas * deltas.new_tensor(stds).view(1, -1) + deltas.new_tensor(means).view(1, -1)
+    stds_t = stds if isinstance(stds, torch.Tensor) else deltas.new_tensor(stds)
+    means_t = means if isinstance(means, torch.Tensor) else deltas.new_tensor(means)
+    d = deltas * stds_t.view(1, -1) + means_t.view(1, -1)
     pxy = (rois[:, :2] + rois[:, 2:]) * 0.5
     pwh = rois[:, 2:] - rois[:, :2]
     dxy_wh = pwh * d[:, :2]
@@ -112,8 +139,21 @@ class RoIStage:
         self.bbox_heads = list(bbox_heads)
         self.mask_head = mask_head
         self.score_fn = score_fn or (lambda s: torch.softmax(s, dim=-1))
+        self._consts = {}                       # per-device constant tensors (built once: nothing is copied H2D in run())
         self.timer: Optional[Callable] = None   # optional: timer(name) -> context manager (bench.py uses CUDA events)
         self.trace: Optional[dict] = None       # optional: filled with the tensors at every op boundary (parity tests)
+
+    def _const(self, dev):
+        c = self._consts.get(dev)
+        if c is None:
+            cfg = self.cfg
+            c = dict(stds=[torch.tensor(s, dtype=torch.float32, device=dev) for s in cfg.stage_stds],
+                     means=torch.zeros(4, dtype=torch.float32, device=dev),
+                     far=torch.tensor([[-4096.0, -4096.0, -4095.0, -4095.0]], device=dev),
+                     labels=torch.arange(cfg.num_classes, device=dev, dtype=torch.int64),
+                     zero=torch.zeros((), device=dev), minus1=torch.full((), -1, dtype=torch.int32, device=dev))
+            self._consts[dev] = c
+        return c
 
     def _t(self, name: str):
         return self.timer(name) if self.timer is not None else contextlib.nullcontext()
@@ -145,6 +185,7 @@ class RoIStage:
         K = rois.shape[0]
         C = cfg.num_classes
         tile_of_roi = rois[:, 0].to(torch.int32)
+        K0 = self._const(dev)
         ms_scores = []
         bbox_pred = None
         for i in range(cfg.num_stages):
@@ -155,11 +196,11 @@ class RoIStage:
             ms_scores.append(cls_score)
             if i < cfg.num_stages - 1:
                 # regress_by_class with reg_class_agnostic=True (mmdet bbox_head.py:459-496)
-                new = delta2bbox(rois[:, 1:], bbox_pred, cfg.stage_stds[i], cfg.img_shape)
+                new = delta2bbox(rois[:, 1:], bbox_pred, K0["stds"][i], cfg.img_shape, means=K0["means"])
                 rois = torch.cat([rois[:, :1], new], dim=1)
         cls_score = sum(ms_scores) / float(len(ms_scores))
         scores = self.score_fn(cls_score)
-        bboxes = delta2bbox(rois[:, 1:], bbox_pred, cfg.stage_stds[-1], cfg.img_shape)
+        bboxes = delta2bbox(rois[:, 1:], bbox_pred, K0["stds"][cfg.num_stages - 1], cfg.img_shape, means=K0["means"])
         bboxes = bboxes / cfg.scale_factor  # rescale=True: detections live in the tile frame
 
         # multiclass_nms for every tile at once (nuhtc/models/bbox_head.py:12-102): class-agnostic boxes are
@@ -167,7 +208,7 @@ class RoIStage:
         # through one grouped NMS launch with the per-image class offsets.
         cand_boxes = bboxes[:, None, :].expand(K, C, 4).reshape(-1, 4)
         cand_scores = scores[:, :C].reshape(-1)
-        cand_labels = torch.arange(C, device=dev, dtype=torch.int64).repeat(K)
+        cand_labels = K0["labels"].repeat(K)
         cand_tile = tile_of_roi.repeat_interleave(C)
         groups = torch.where(cand_scores > cfg.score_thr, cand_tile, torch.full_like(cand_tile, -1))
         if max_rois_per_tile is None:
@@ -176,22 +217,31 @@ class RoIStage:
             keep, gstart, gcount, status = nms_groups(cand_boxes, cand_scores, cand_labels, groups, B, max_rois_per_tile * C,
                                                       cfg.nms_iou, 0, "offset")
         self._rec(nms_boxes=bboxes, nms_scores=scores, nms_keep=keep, nms_start=gstart, nms_count=gcount)
-        # max_per_img truncation; one small D2H of the per-tile counts sizes the mask branch
-        cnt = torch.clamp(gcount, max=cfg.max_per_img) if cfg.max_per_img > 0 else gcount
-        host = torch.stack([gstart, cnt]).cpu()
-        if int(status.item()) != 0:
-            raise RuntimeError(f"nms_groups status {int(status.item())}: a tile exceeded max_rois_per_tile*num_classes")
-        sel = torch.cat([torch.arange(s, s + c, device=dev) for s, c in zip(host[0].tolist(), host[1].tolist())]) \
-            if int(host[1].sum()) > 0 else torch.zeros(0, dtype=torch.int64, device=dev)
-        det_cand = keep[sel]
-        det_boxes = cand_boxes[det_cand].contiguous()
-        det_scores = cand_scores[det_cand].contiguous()
+        # max_per_img truncation WITHOUT a host round trip: every tile gets max_per_img detection slots; slot r of tile
+        # b is its r-th kept candidate (score order) or invalid.  Invalid slots carry a box far outside the frame (RoIAlign
+        # and paste see nothing there) and tile -1 (the mask NMS ignores them), so no kernel needs the counts on the host.
+        N = keep.numel()
+        if cfg.max_per_img > 0:
+            M = cfg.max_per_img
+            r = torch.arange(M, device=dev)
+            cnt = torch.clamp(gcount, max=M)
+            det_valid = (r[None, :] < cnt[:, None]).reshape(-1)
+            idx = (gstart[:, None] + r[None, :]).clamp(max=N - 1).reshape(-1)
+            det_cand = torch.where(det_valid, keep[idx], torch.zeros_like(idx))
+        else:  # unbounded detections per tile: sizes are data dependent, read them back
+            host = torch.stack([gstart, gcount]).cpu()
+            idx = torch.cat([torch.arange(s_, s_ + c_, device=dev) for s_, c_ in zip(host[0].tolist(), host[1].tolist())]) \
+                if int(host[1].sum()) > 0 else torch.zeros(0, dtype=torch.int64, device=dev)
+            det_cand = keep[idx]
+            det_valid = torch.ones_like(det_cand, dtype=torch.bool)
+        det_boxes = torch.where(det_valid[:, None], cand_boxes[det_cand], K0["far"]).contiguous()
+        det_scores = torch.where(det_valid, cand_scores[det_cand], K0["zero"]).contiguous()
         det_labels = cand_labels[det_cand]
-        det_tile = cand_tile[det_cand].contiguous()
+        det_tile = torch.where(det_valid, cand_tile[det_cand], K0["minus1"]).contiguous()
         D = det_boxes.shape[0]
 
         # mask branch: RoIAlign 14x14 on the detections (network frame), mask head, paste into the tile frame
-        mask_rois = torch.cat([det_tile.to(torch.float32)[:, None], det_boxes * cfg.scale_factor], dim=1)
+        mask_rois = torch.cat([det_tile.clamp(min=0).to(torch.float32)[:, None], det_boxes * cfg.scale_factor], dim=1)
         with self._t("roi_align_mask"):
             mask_feats = self.extract(feats, mask_rois, cfg.mask_out, cfg.mask_sampling_ratio)
         self._rec(mask_rois=mask_rois, mask_feats=mask_feats)
@@ -218,4 +268,5 @@ class RoIStage:
             keep2, tstart, tcount, st2 = mask_nms_device(bits, area, bbox, det_scores, W, cfg.mask_nms_thr, tile=tile_ids,
                                                          num_tiles=B, max_tile_size=cap)
         self._rec(mnms_tile=tile_ids)
-        return RoIStageResult(det_boxes, det_scores, det_labels, det_tile, masks, bits, area, keep2, tstart, tcount)
+        return RoIStageResult(det_boxes, det_scores, det_labels, det_tile, masks, bits, area, keep2, tstart, tcount,
+                              det_valid=det_valid, det_cand=det_cand, status=(status, st2))

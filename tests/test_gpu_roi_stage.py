@@ -30,7 +30,8 @@ def test_stage_op_boundaries(oracle, extractor, C, sr):
     gh = copy.copy(heads).to("cuda")
     st = RoIStage(cfg, gh.bbox_heads(), gh.mask_head)
     st.trace = {}
-    res = st.run([f.cuda() for f in feats], rois.cuda())
+    raw = st.run([f.cuda() for f in feats], rois.cuda())   # slot form: max_per_img slots per tile, no host sync inside
+    res = raw.compact()
     tr = st.trace
     ext = (lambda r, P, s: oracle.single_roi_extract(feats, r, cfg.featmap_strides, P, s)) if extractor == "single" else \
           (lambda r, P, s: oracle.sum_roi_extract(feats[:2], r, cfg.featmap_strides[:2], P, s))
@@ -61,15 +62,16 @@ def test_stage_op_boundaries(oracle, extractor, C, sr):
     # paste + threshold
     probs, pb = tr["paste_probs"][0].cpu(), tr["paste_boxes"][0].cpu()
     refp = oracle.paste_masks(probs, pb, 256, 256)
-    diff = res.masks.cpu() != (refp >= 0.5)
+    diff = raw.masks.cpu() != (refp >= 0.5)
     assert ((refp - 0.5).abs()[diff] <= 1e-6).all()
-    # mask NMS per tile on the GPU's own masks
-    m = res.masks.cpu().numpy().astype(np.uint8)
+    assert not raw.masks[~raw.det_valid].any()                      # padding slots paste nothing
+    # mask NMS per tile on the GPU's own masks (slot indices)
+    m = raw.masks.cpu().numpy().astype(np.uint8)
     tid = tr["mnms_tile"][0].cpu().numpy()
-    kept = res.kept_indices()
+    kept = raw.kept_indices()
     for b in range(feats[0].shape[0]):
         sel = np.nonzero(tid == b)[0]
-        ref = sel[oracle.mask_nms(m[sel], res.det_scores.cpu().numpy()[sel], thr=0.05)] if len(sel) else sel
+        ref = sel[oracle.mask_nms(m[sel], raw.det_scores.cpu().numpy()[sel], thr=0.05)] if len(sel) else sel
         assert (kept[b].cpu().numpy() == ref).all()
         assert len(ref) > 0
 
@@ -82,7 +84,7 @@ def test_stage_end_to_end_vs_reference_flow(oracle):
     cfg, feats, rois, heads = _setup("single", 64, B=2, n_per=250, max_per_img=80)
     gh = copy.copy(heads).to("cuda")
     st = RoIStage(cfg, gh.bbox_heads(), gh.mask_head)
-    res = st.run([f.cuda() for f in feats], rois.cuda())
+    res = st.run([f.cuda() for f in feats], rois.cuda()).compact()
     ref = roi_stage_cpu(feats, rois, heads.bbox_heads(), heads.mask_head, cfg)
     kept = res.kept_indices()
     tile = res.det_tile.cpu().numpy()
@@ -103,6 +105,7 @@ def test_bits_lane_equals_dense_lane():
     heads.to("cuda")
     f = [x.cuda() for x in feats]
     a = RoIStage(cfg, heads.bbox_heads(), heads.mask_head).run(f, rois.cuda())
+    a.check()
     cfg2 = copy.copy(cfg)
     cfg2.dense_masks = False
     b = RoIStage(cfg2, heads.bbox_heads(), heads.mask_head).run(f, rois.cuda())
