@@ -49,7 +49,8 @@ constexpr int kScanThreads = 1024;
 template <typename OutT>
 __global__ void __launch_bounds__(kScanThreads) greedy_scan_kernel(const uint64_t *__restrict__ mask, const int32_t *__restrict__ svals,
                                                                    const int *__restrict__ seg_start, int wpr,
-                                                                   OutT *__restrict__ keep, OutT *__restrict__ group_count) {
+                                                                   OutT *__restrict__ keep, OutT *__restrict__ group_count,
+                                                                   const uint64_t *__restrict__ skeys, uint64_t *__restrict__ kkeys) {
     extern __shared__ unsigned long long removed[]; // [wpr]
     __shared__ unsigned long long s_diag[64];
     __shared__ unsigned long long s_keepbits;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kScanThreads) greedy_scan_kernel(const uint64_
         if (tid < 64 && ((kb >> tid) & 1ull)) {
             const int rank = __popcll(kb & ((1ull << tid) - 1ull));
             keep[s0 + kept + rank] = (OutT)svals[s0 + c * 64 + tid];
+            if (kkeys) kkeys[s0 + kept + rank] = skeys[s0 + c * 64 + tid]; // sort key of the kept row (segment merge)
         }
         kept += __popcll(kb);
         // OR the kept rows into `removed` for the words to the right of the diagonal.
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kScanThreads) greedy_scan_kernel(const uint64_
 
 template <typename OutT>
 static int launch_greedy_scan(const uint64_t *mask, const int32_t *svals, const int *seg_start, int wpr, int G, OutT *keep,
-                              OutT *group_count, cudaStream_t st) {
+                              OutT *group_count, cudaStream_t st, const uint64_t *skeys = nullptr, uint64_t *kkeys = nullptr) {
     static bool attr_done = false;
     if ((size_t)wpr * 8 > 200 * 1024) {
         nuhtc_set_error("greedy scan: segment too large for the shared removed-set");
@@ -119,7 +121,7 @@ static int launch_greedy_scan(const uint64_t *mask, const int32_t *svals, const 
         NUHTC_CUDA(cudaFuncSetAttribute(greedy_scan_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
-    greedy_scan_kernel<OutT><<<G, kScanThreads, (size_t)wpr * 8, st>>>(mask, svals, seg_start, wpr, keep, group_count);
+    greedy_scan_kernel<OutT><<<G, kScanThreads, (size_t)wpr * 8, st>>>(mask, svals, seg_start, wpr, keep, group_count, skeys, kkeys);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }

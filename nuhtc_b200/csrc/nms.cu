@@ -33,13 +33,42 @@ __device__ __forceinline__ int float_ordered_int(float f) {
 }
 __device__ __forceinline__ float ordered_int_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__global__ void nms_init_kernel(int *cnt, int *gmax, int G, int32_t *status) {
+__global__ void nms_init_kernel(int *cnt, int *gmax, int nseg, int ngroup, int32_t *status) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < G) {
-        cnt[i] = 0;
-        gmax[i] = float_ordered_int(-INFINITY);
-    }
+    if (i < nseg) cnt[i] = 0;
+    if (i < ngroup) gmax[i] = float_ordered_int(-INFINITY);
     if (i == 0) *status = 0;
+}
+
+// class-segmented variant: the sort segment is (group, label); only the per-group max coordinate stays per group
+__global__ void __launch_bounds__(256) nms_prep_seg_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores,
+                                                           const int64_t *__restrict__ labels, const int32_t *__restrict__ groups,
+                                                           int64_t N, int G, int Cn, int need_max, int need_nonneg,
+                                                           uint64_t *__restrict__ keys, int32_t *__restrict__ vals, int *cnt,
+                                                           int *gmax, int32_t *status) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int g = groups ? groups[i] : 0;
+    const long long lab = labels[i];
+    int seg;
+    if (g < 0) {
+        seg = G * Cn; // not a candidate
+    } else if (g >= G || lab < 0 || lab >= Cn) {
+        atomicExch(status, 2);
+        seg = G * Cn;
+        g = -1;
+    } else {
+        seg = g * Cn + (int)lab;
+    }
+    keys[i] = ((uint64_t)(uint32_t)seg << 32) | float_desc_key(scores[i]);
+    vals[i] = (int32_t)i;
+    atomicAdd(cnt + seg, 1);
+    if (g >= 0 && (need_max || need_nonneg)) {
+        const float4 b = boxes[i];
+        if (need_max) atomicMax(gmax + g, float_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+        // class segments are only equivalent to the all-pairs test on offset boxes when no coordinate is negative
+        if (need_nonneg && fminf(fminf(b.x, b.y), fminf(b.z, b.w)) < 0.f) atomicExch(status, 3);
+    }
 }
 
 __global__ void __launch_bounds__(256) nms_prep_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores,
@@ -83,7 +112,7 @@ __global__ void __launch_bounds__(256) nms_prep_kernel(const float4 *__restrict_
 
 __global__ void __launch_bounds__(256) nms_gather_kernel(const float4 *__restrict__ boxes, const int64_t *__restrict__ labels,
                                                          const uint64_t *__restrict__ skeys, const int32_t *__restrict__ svals,
-                                                         const int *__restrict__ gmax, int64_t N, int mode, float fo,
+                                                         const int *__restrict__ gmax, int64_t N, int mode, float fo, int seg_div,
                                                          float4 *__restrict__ sbox, float *__restrict__ sarea,
                                                          int32_t *__restrict__ slab) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -93,7 +122,7 @@ __global__ void __launch_bounds__(256) nms_gather_kernel(const float4 *__restric
     int lab = 0;
     if (mode != NUHTC_NMS_AGNOSTIC) lab = (int)labels[i];
     if (mode == NUHTC_NMS_OFFSET || mode == NUHTC_NMS_PERCLASS) {
-        const int g = (int)(skeys[p] >> 32);
+        const int g = (int)(skeys[p] >> 32) / seg_div; // seg_div = classes per group when class-segmented, else 1
         // batched_nms: offsets = idxs.to(boxes) * (boxes.max() + 1); boxes_for_nms = boxes + offsets[:, None]
         const float off = __fmul_rn((float)labels[i], __fadd_rn(ordered_int_float(gmax[g]), 1.0f));
         b.x = __fadd_rn(b.x, off);
@@ -178,6 +207,47 @@ __global__ void __launch_bounds__(kMaskWarps * 32) nms_mask_kernel(const float4 
     }
 }
 
+// class-segmented NMS leaves one score-sorted kept list per (group, class); the group's list is their merge.  The rank of
+// a kept box inside its group = its rank in its own list + the number of boxes of the other classes that sort before it
+// (binary search on (score key, index), the order of the radix sort).
+__global__ void __launch_bounds__(256) nms_merge_segments_kernel(const uint64_t *__restrict__ skeys, const int *__restrict__ seg_start,
+                                                                const int64_t *__restrict__ seg_count, const int64_t *__restrict__ keep_seg,
+                                                                const uint64_t *__restrict__ kkeys, int64_t N, int G, int Cn,
+                                                                int64_t *__restrict__ keep, int64_t *__restrict__ group_start,
+                                                                int64_t *__restrict__ group_count) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < G) {
+        int64_t tot = 0;
+        for (int c = 0; c < Cn; ++c) tot += seg_count[p * Cn + c];
+        group_start[p] = seg_start[p * Cn];
+        group_count[p] = tot;
+    }
+    if (p >= N) return;
+    const int seg = (int)(skeys[p] >> 32);
+    if (seg >= G * Cn) return;
+    const int r = (int)(p - seg_start[seg]);
+    if (r >= seg_count[seg]) return;
+    const int s0 = seg_start[seg];
+    const uint32_t key = (uint32_t)kkeys[s0 + r];
+    const int64_t idx = keep_seg[s0 + r];
+    const int g = seg / Cn;
+    int rank = r;
+    for (int c = 0; c < Cn; ++c) {
+        const int o = g * Cn + c;
+        if (o == seg) continue;
+        const int b0 = seg_start[o];
+        int lo = 0, hi = (int)seg_count[o];
+        while (lo < hi) { // first element of list o that does not sort before (key, idx)
+            const int mid = (lo + hi) >> 1;
+            const uint32_t k2 = (uint32_t)kkeys[b0 + mid];
+            const bool before = k2 < key || (k2 == key && keep_seg[b0 + mid] < idx);
+            if (before) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    keep[seg_start[g * Cn] + rank] = idx;
+}
+
 struct NmsWs {
     uint64_t *keys_in, *keys_out;
     int32_t *vals_in, *vals_out;
@@ -186,6 +256,8 @@ struct NmsWs {
     int32_t *slab;
     int *cnt, *gmax, *seg_start;
     uint64_t *mask;
+    int64_t *keep_seg, *seg_count; // class-segmented path
+    uint64_t *kkeys;
     void *cub_tmp;
     size_t cub_bytes;
     size_t total;
@@ -198,7 +270,7 @@ static size_t cub_sort_bytes(int64_t N) {
     return bytes;
 }
 
-static NmsWs nms_layout(void *ws, int64_t N, int G, int64_t M) {
+static NmsWs nms_layout(void *ws, int64_t N, int G, int64_t M, int Cn = 0) {
     NmsWs L;
     char *p = (char *)ws;
     size_t off = 0;
@@ -215,10 +287,14 @@ static NmsWs nms_layout(void *ws, int64_t N, int G, int64_t M) {
     L.sbox = (float4 *)take(sizeof(float4) * N);
     L.sarea = (float *)take(sizeof(float) * N);
     L.slab = (int32_t *)take(sizeof(int32_t) * N);
-    L.cnt = (int *)take(sizeof(int) * (G + 1));
+    const int S = Cn > 0 ? G * Cn : G; // sort segments
+    L.cnt = (int *)take(sizeof(int) * (S + 1));
     L.gmax = (int *)take(sizeof(int) * (G + 1));
-    L.seg_start = (int *)take(sizeof(int) * (G + 1));
+    L.seg_start = (int *)take(sizeof(int) * (S + 1));
     L.mask = (uint64_t *)take(sizeof(uint64_t) * (size_t)N * wpr);
+    L.keep_seg = (int64_t *)take(Cn > 0 ? sizeof(int64_t) * N : 8);
+    L.seg_count = (int64_t *)take(sizeof(int64_t) * (S + 1));
+    L.kkeys = (uint64_t *)take(Cn > 0 ? sizeof(uint64_t) * N : 8);
     L.cub_bytes = cub_sort_bytes(N);
     L.cub_tmp = take(L.cub_bytes);
     L.total = off;
@@ -227,15 +303,15 @@ static NmsWs nms_layout(void *ws, int64_t N, int G, int64_t M) {
 
 } // namespace
 
-NUHTC_API size_t nuhtc_nms_workspace_bytes(int64_t N, int num_groups, int64_t max_group_size) {
+NUHTC_API size_t nuhtc_nms_workspace_bytes(int64_t N, int num_groups, int64_t max_group_size, int num_classes) {
     if (N <= 0 || num_groups <= 0) return 256;
     if (max_group_size > N) max_group_size = N;
     if (max_group_size < 1) max_group_size = 1;
-    return nms_layout(nullptr, N, num_groups, max_group_size).total;
+    return nms_layout(nullptr, N, num_groups, max_group_size, num_classes > 0 ? num_classes : 0).total;
 }
 
 NUHTC_API int nuhtc_nms(const float *boxes, const float *scores, const int64_t *labels, const int32_t *groups, int64_t N,
-                        int num_groups, int64_t max_group_size, float iou_thr, int offset, int mode, int64_t *keep,
+                        int num_groups, int64_t max_group_size, float iou_thr, int offset, int mode, int num_classes, int64_t *keep,
                         int64_t *group_start, int64_t *group_count, int32_t *status, void *ws, size_t ws_bytes, void *stream) {
     NUHTC_CHECK_ARG(N >= 0 && N < (1ll << 31), "nms: N=%lld out of range", (long long)N);
     NUHTC_CHECK_ARG(num_groups >= 1 && num_groups <= 65535, "nms: num_groups=%d out of range", num_groups);
@@ -255,7 +331,9 @@ NUHTC_API int nuhtc_nms(const float *boxes, const float *scores, const int64_t *
     if (max_group_size > N) max_group_size = N;
     if (max_group_size < 1) max_group_size = 1;
     const int G = num_groups;
-    NmsWs L = nms_layout(ws, N, G, max_group_size);
+    const int Cn = (num_classes > 0 && mode != NUHTC_NMS_AGNOSTIC) ? num_classes : 0; // class segments
+    NUHTC_CHECK_ARG(Cn == 0 || (long)G * Cn <= 65535, "nms: num_groups*num_classes=%ld too large", (long)G * Cn);
+    NmsWs L = nms_layout(ws, N, G, max_group_size, Cn);
     if (L.total > ws_bytes) {
         nuhtc_set_error("nms: workspace %zu < required %zu", ws_bytes, L.total);
         return NUHTC_EWORKSPACE;
@@ -265,19 +343,33 @@ NUHTC_API int nuhtc_nms(const float *boxes, const float *scores, const int64_t *
     NUHTC_CHECK_ARG((size_t)wpr * 8 <= 200 * 1024, "nms: group too large for the shared removed-set");
     const float fo = (float)offset;
     const int nb = (int)((N + 255) / 256);
-    nms_init_kernel<<<(G + 256) / 256, 256, 0, st>>>(L.cnt, L.gmax, G + 1, status);
-    nms_prep_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, groups, N, G, mode == NUHTC_NMS_OFFSET || mode == NUHTC_NMS_PERCLASS, L.keys_in,
-                                        L.vals_in, L.cnt, L.gmax, status);
-    segments_kernel<int64_t><<<1, 256, 0, st>>>(L.cnt, G, max_group_size, L.seg_start, group_start, status);
+    const int S = Cn > 0 ? G * Cn : G;
+    const bool offs = mode == NUHTC_NMS_OFFSET || mode == NUHTC_NMS_PERCLASS;
+    nms_init_kernel<<<(S + 256) / 256, 256, 0, st>>>(L.cnt, L.gmax, S + 1, G + 1, status);
+    if (Cn > 0)
+        nms_prep_seg_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, labels, groups, N, G, Cn, offs, mode == NUHTC_NMS_OFFSET,
+                                                L.keys_in, L.vals_in, L.cnt, L.gmax, status);
+    else
+        nms_prep_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, groups, N, G, offs, L.keys_in, L.vals_in, L.cnt, L.gmax, status);
+    segments_kernel<int64_t><<<1, 256, 0, st>>>(L.cnt, S, max_group_size, L.seg_start, Cn > 0 ? L.seg_count : group_start, status);
     int gbits = 0;
-    while ((1 << gbits) < G + 1) ++gbits;
+    while ((1 << gbits) < S + 1) ++gbits;
     size_t cub_bytes = L.cub_bytes;
     NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, N, 0,
                                                32 + gbits, st));
-    nms_gather_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, labels, L.keys_out, L.vals_out, L.gmax, N, mode, fo, L.sbox,
-                                          L.sarea, L.slab);
-    dim3 mgrid((wpr + kMaskWarps - 1) / kMaskWarps, wpr, G);
+    nms_gather_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, labels, L.keys_out, L.vals_out, L.gmax, N, mode, fo, Cn > 0 ? Cn : 1,
+                                          L.sbox, L.sarea, L.slab);
+    dim3 mgrid((wpr + kMaskWarps - 1) / kMaskWarps, wpr, S);
     nms_mask_kernel<<<mgrid, kMaskWarps * 32, 0, st>>>(L.sbox, L.sarea, L.slab, L.seg_start, wpr, mode, fo, iou_thr, L.mask);
     NUHTC_LAUNCH_CHECK();
+    if (Cn > 0) {
+        int rc = launch_greedy_scan<int64_t>(L.mask, L.vals_out, L.seg_start, wpr, S, L.keep_seg, L.seg_count, st, L.keys_out, L.kkeys);
+        if (rc) return rc;
+        const long nt = N > G ? N : G;
+        nms_merge_segments_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(L.keys_out, L.seg_start, L.seg_count, L.keep_seg, L.kkeys, N,
+                                                                              G, Cn, keep, group_start, group_count);
+        NUHTC_LAUNCH_CHECK();
+        return NUHTC_OK;
+    }
     return launch_greedy_scan<int64_t>(L.mask, L.vals_out, L.seg_start, wpr, G, keep, group_count, st);
 }

@@ -160,8 +160,12 @@ _MODE = {"agnostic": L.NMS_AGNOSTIC, "offset": L.NMS_OFFSET, "perclass": L.NMS_P
 
 
 def nms_groups(boxes: torch.Tensor, scores: torch.Tensor, labels: Optional[torch.Tensor], groups: Optional[torch.Tensor],
-               num_groups: int, max_group_size: int, iou_threshold: float, offset: int = 0, mode: str = "agnostic"):
+               num_groups: int, max_group_size: int, iou_threshold: float, offset: int = 0, mode: str = "agnostic",
+               num_classes: int = 0):
     """Batched greedy NMS over independent groups (images), no host sync.
+
+    ``num_classes`` > 0 sorts into (group, class) segments (labels < num_classes): same result, 5x less work for 5
+    classes.  With mode 'offset' that requires non-negative box coordinates (status 3 otherwise, see the header).
 
     Returns (keep [N] int64, group_start [G] int64, group_count [G] int64, status [1] int32), all on the device:
     group g's kept original indices, score-descending, are keep[group_start[g] : group_start[g]+group_count[g]]."""
@@ -181,12 +185,13 @@ def nms_groups(boxes: torch.Tensor, scores: torch.Tensor, labels: Optional[torch
     gcount = torch.empty(num_groups, dtype=torch.int64, device=dev)
     status = torch.empty(1, dtype=torch.int32, device=dev)
     lib = L.lib()
-    wsb = lib.nuhtc_nms_workspace_bytes(N, num_groups, max_group_size)
+    ncls = int(num_classes) if mode != "agnostic" else 0
+    wsb = lib.nuhtc_nms_workspace_bytes(N, num_groups, max_group_size, ncls)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.nuhtc_nms(boxes.data_ptr(), scores.data_ptr(), L.ptr(labels), L.ptr(groups), N, num_groups, max_group_size,
-                           float(iou_threshold), int(offset), _MODE[mode], keep.data_ptr(), gstart.data_ptr(), gcount.data_ptr(),
-                           status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev))
+                           float(iou_threshold), int(offset), _MODE[mode], ncls, keep.data_ptr(), gstart.data_ptr(),
+                           gcount.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev))
     L.check(rc, "nms")
     L.count("nms")
     return keep, gstart, gcount, status
@@ -196,7 +201,14 @@ def _nms_single(boxes, scores, labels, iou_threshold, offset, mode) -> torch.Ten
     N = boxes.size(0)
     if N == 0:
         return torch.empty(0, dtype=torch.int64, device=boxes.device)
-    keep, _, gcount, status = nms_groups(boxes, scores, labels, None, 1, N, iou_threshold, offset, mode)
+    ncls = 0
+    if mode in ("perclass", "perclass_raw") and labels is not None:
+        # one NMS per class id, exactly mmcv's loop: the ids become sort segments (dense ids 0..n-1 expected; a sparse id
+        # space just leaves empty segments)
+        top = int(labels.max().item()) + 1
+        if int(labels.min().item()) >= 0 and top <= 4096:
+            ncls = top
+    keep, _, gcount, status = nms_groups(boxes, scores, labels, None, 1, N, iou_threshold, offset, mode, num_classes=ncls)
     k = int(gcount.item())  # the op returns a data-dependent shape, as mmcv's does
     return keep[:k]
 

@@ -214,8 +214,9 @@ class RoIStage:
         if max_rois_per_tile is None:
             max_rois_per_tile = int(torch.bincount(tile_of_roi.long(), minlength=B).max().item())
         with self._t("nms"):
+            # decoded boxes are clamped to the frame (max_shape), so no coordinate is negative: class segments are exact
             keep, gstart, gcount, status = nms_groups(cand_boxes, cand_scores, cand_labels, groups, B, max_rois_per_tile * C,
-                                                      cfg.nms_iou, 0, "offset")
+                                                      cfg.nms_iou, 0, "offset", num_classes=C)
         self._rec(nms_boxes=bboxes, nms_scores=scores, nms_keep=keep, nms_start=gstart, nms_count=gcount)
         # max_per_img truncation WITHOUT a host round trip: every tile gets max_per_img detection slots; slot r of tile
         # b is its r-th kept candidate (score order) or invalid.  Invalid slots carry a box far outside the frame (RoIAlign

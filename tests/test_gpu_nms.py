@@ -121,3 +121,36 @@ def test_large_sweep_properties(N):
     iou = torchvision.ops.box_iou((b + off)[didx], (b + off)[keep])
     higher = s[keep][None, :] > s[didx][:, None]
     assert ((iou > 0.5) & higher).any(dim=1).all()
+
+
+def test_class_segmented_nms_equals_all_pairs(oracle):
+    """(group, class) sort segments give the same keep lists as the all-pairs test on offset boxes when no coordinate
+    is negative; a negative coordinate is reported through status 3."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    G = 6
+    bs, ss, ls, gs = [], [], [], []
+    for g in range(G):
+        b, s, l = synth.nms_boxes(900 + 31 * g, seed=200 + g)
+        bs.append(b); ss.append(s); ls.append(l); gs.append(torch.full((b.shape[0],), g, dtype=torch.int32))
+    B, S, Lb, Gp = torch.cat(bs), torch.cat(ss), torch.cat(ls), torch.cat(gs)
+    B = B + 20.0   # the generator centres boxes on [0, side]: shift so that no coordinate is negative
+    Gp[::17] = -1  # some candidates are not candidates at all
+    perm = torch.randperm(B.shape[0], generator=torch.Generator().manual_seed(2))
+    B, S, Lb, Gp = B[perm], S[perm], Lb[perm], Gp[perm]
+    args = (B.cuda(), S.cuda(), Lb.cuda(), Gp.cuda(), G, 1200, 0.5, 0, "offset")
+    k0, s0, c0, st0 = nb.nms_groups(*args)
+    k1, s1, c1, st1 = nb.nms_groups(*args, num_classes=5)
+    assert int(st0.item()) == 0 and int(st1.item()) == 0
+    assert torch.equal(c0, c1)
+    for g in range(G):
+        a = k0[s0[g]: s0[g] + c0[g]]
+        b = k1[s1[g]: s1[g] + c1[g]]
+        assert torch.equal(a, b), g
+        idx = (Gp == g).nonzero().squeeze(1)
+        _, k_ref = oracle.batched_nms(B[idx], S[idx], Lb[idx], dict(type="nms", iou_threshold=0.5))
+        assert torch.equal(b.cpu(), idx[k_ref]), g
+    Bn = B.clone()
+    Bn[int((Gp >= 0).nonzero()[3])] -= 40.0
+    _, _, _, st = nb.nms_groups(Bn.cuda(), S.cuda(), Lb.cuda(), Gp.cuda(), G, 1200, 0.5, 0, "offset", num_classes=5)
+    assert int(st.item()) == 3
