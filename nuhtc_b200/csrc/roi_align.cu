@@ -17,7 +17,9 @@
 //    column, which is what lets the kernel run at the HBM write rate instead of the L1 rate.
 //  * roi_align_direct_kernel -- literal per-sample restatement (any layout / shape), same float op
 //    order as the CPU reference; used as fallback and as an on-device cross-check.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -512,6 +514,21 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
 
 constexpr int kPipeMaxRows = 40; // staged windows taller than this take the direct path
 
+// 2-D TMA tensor maps of the NHWC levels: dim0 = channels, dim1 = pixels (B*H*W); box = {CC channels, WBOX pixels}.
+// They let a CTA that owns only CC of the C channels fetch a window row with ONE instruction (cp.async.bulk.tensor,
+// UTMALDG) instead of one small bulk copy per pixel.
+constexpr int kTmapLevels = 4;
+constexpr int kTmapBoxes = 4;
+__host__ __device__ constexpr int tmap_box_px(int v) { return 8 * (v + 1); } // 8, 16, 24, 32 pixels
+struct RoiTmaps {
+    CUtensorMap m[kTmapLevels][kTmapBoxes];
+};
+__device__ __forceinline__ void tma_tensor2d_g2s(uint32_t dst, const CUtensorMap *map, int c0, int p0, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(p0), "r"(bar)
+                 : "memory");
+}
+
 template <int P>
 struct PipeSlot { // tap tables + geometry of one work item
     float wx[P][kMaxTap];
@@ -597,7 +614,7 @@ __device__ __forceinline__ void staged_rows(const float *ring, int stage_floats,
 template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
 __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
     roi_align_pipe_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int K, int sr, int aligned, int mode, float finest,
-                          float *__restrict__ out, int bulk_store_flag) {
+                          float *__restrict__ out, int bulk_store_flag, const __grid_constant__ RoiTmaps tm) {
     constexpr int CC = NQ * 4;
     constexpr int PP = SepCfg<P>::PP;
     const bool kBulkStore = (SepCfg<P>::S == PP) && bulk_store_flag != 0;            // contiguous tile == contiguous global chunk
@@ -631,7 +648,8 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
 
     const int nchunk = C / CC;
     const int nlev = mode == NUHTC_ROI_ROUTE ? 1 : lv.L;
-    const long nunits = (long)K * nchunk; // a unit = (RoI, channel chunk); its levels are consecutive items
+    const long nunits = K; // a unit = one RoI: its levels are consecutive items, its channel chunks share the item's tables
+                           // (nchunk > 1 is only launched with nlev == 1)
     unsigned itemctr = 0;
     constexpr int WYS = (P + 6) / 7 * 8;
     static_assert(PB <= 7, "a consumer owns at most 7 output rows");
@@ -645,27 +663,30 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                 const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
                 mbar_wait(tfull0 + 8 * slot, use & 1);
                 const PipeSlot<P> &sl = s_slot[slot];
-                const int md = sl.mode, x0 = sl.x0, ww = sl.ww, y0 = sl.y0, y1 = sl.y1, l = sl.level, b = sl.batch, c0 = sl.c0;
+                const int md = sl.mode, x0 = sl.x0, ww = sl.ww, y0 = sl.y0, y1 = sl.y1, l = sl.level, b = sl.batch;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * slot); // the slot's geometry is in registers now
                 if (md == kPipeStaged && y1 > y0) {
                     const int H = lv.H[l], W = lv.W[l];
-                    const float *src0 = lv.data[l] + (((size_t)b * H + y0) * W + x0) * (size_t)C + c0;
                     const size_t rstride = (size_t)W * C;
-                    for (int y = y0; y < y1; ++y, rp.next<NS>()) {
-                        const unsigned stage = rp.stage;
-                        mbar_wait(empty0 + 8 * stage, rp.parity ^ 1u);
-                        const uint32_t dst = smem_u32(s_ring + (size_t)stage * STAGE_FLOATS);
-                        const float *src = src0 + (size_t)(y - y0) * rstride;
-                        if (nchunk == 1) { // the row segment is contiguous in NHWC
+                    const int bv = (ww + 7) / 8 - 1; // smallest tensor-map box that covers the row
+                    for (int chunk = 0; chunk < nchunk; ++chunk) {
+                        const int c0 = chunk * CC;
+                        const float *src0 = lv.data[l] + (((size_t)b * H + y0) * W + x0) * (size_t)C + c0;
+                        const int pix0 = (b * H + y0) * W + x0;
+                        for (int y = y0; y < y1; ++y, rp.next<NS>()) {
+                            const unsigned stage = rp.stage;
+                            mbar_wait(empty0 + 8 * stage, rp.parity ^ 1u);
+                            const uint32_t dst = smem_u32(s_ring + (size_t)stage * STAGE_FLOATS);
                             if (lane == 0) {
-                                mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)ww * CC * 4);
-                                tma_bulk_g2s(dst, src, (uint32_t)ww * CC * 4, full0 + 8 * stage);
+                                if (nchunk == 1) { // the row segment is contiguous in NHWC: one plain bulk copy
+                                    mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)ww * CC * 4);
+                                    tma_bulk_g2s(dst, src0 + (size_t)(y - y0) * rstride, (uint32_t)ww * CC * 4, full0 + 8 * stage);
+                                } else {           // CC of the C channels: one 2-D tensor copy of {CC, box} elements
+                                    mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)tmap_box_px(bv) * CC * 4);
+                                    tma_tensor2d_g2s(dst, &tm.m[l][bv], c0, pix0 + (y - y0) * W, full0 + 8 * stage);
+                                }
                             }
-                        } else {           // one CC-channel piece per pixel
-                            if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)ww * CC * 4);
-                            for (int x = lane; x < ww; x += 32)
-                                tma_bulk_g2s(dst + (uint32_t)x * CC * 4, src + (size_t)x * C, CC * 4, full0 + 8 * stage);
                         }
                     }
                 }
@@ -677,8 +698,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
         // =========================== tap warp: tables + window geometry, kPipeSlots items ahead ===========================
         const int lane = tid - NCONS;
         for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-            const int chunk = (int)(unit % nchunk);
-            const int k = (int)(unit / nchunk);
+            const int k = (int)unit;
             const float *roi = rois + (size_t)k * 5;
             for (int it = 0; it < nlev; ++it, ++itemctr) {
                 const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
@@ -738,7 +758,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                     sl.level = l;
                     sl.batch = g.b;
                     sl.k = k;
-                    sl.c0 = chunk * CC;
+                    sl.c0 = 0;
                     sl.last = it == nlev - 1;
                 }
                 mbar_arrive(tfull0 + 8 * slot); // all 32 lanes arrive: each releases its own table writes
@@ -764,93 +784,8 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
     int toff[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) toff[jj] = (4 * q + ((jj + rot) & 3)) * S + ph0 * P + pw;
-    for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-        int k = 0, c0 = 0;
-        for (int it = 0; it < nlev; ++it, ++itemctr) {
-            const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
-            mbar_wait(tfull0 + 8 * slot, use & 1);
-            const PipeSlot<P> &sl = s_slot[slot];
-            const int md = sl.mode, y0 = sl.y0, y1 = sl.y1, l = sl.level;
-            k = sl.k;
-            c0 = sl.c0;
-            const int nx = sl.nx[pw];
-            int ys[PB], ny[PB];
-            int my0 = 1 << 30, my1 = -1;
-#pragma unroll
-            for (int i = 0; i < PB; ++i) {
-                ys[i] = sl.ys[ph0 + i];
-                ny[i] = sl.ny[ph0 + i];
-                if (ny[i] > 0) {
-                    my0 = min(my0, ys[i]);
-                    my1 = max(my1, ys[i] + ny[i]);
-                }
-            }
-            const float *wxp = sl.wx[pw], *wyp = sl.wy[ph0];
-            if (!worker) { my0 = 0; my1 = 0; }
-            if (md == kPipeStaged) {
-                if (y1 > y0) {
-                    const int xoff = sl.xs[pw] - sl.x0;
-                    if (nx <= 0) { my0 = 0; my1 = 0; } // no valid sample in this column: still take part in the row barriers
-                    const float *wyd = &sl.wyd[0][ph0 / 7 * 8];
-                    switch (nx) {
-                        case 1: staged_rows<1, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                        case 2: staged_rows<2, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                        case 3: staged_rows<3, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                        case 4: staged_rows<4, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                        default: staged_rows<0, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx > 0 ? nx : 0, my0, my1); break;
-                    }
-                }
-            } else if (worker) {
-                const int H = lv.H[l], W = lv.W[l];
-                const float *img = lv.data[l] + (size_t)sl.batch * H * W * C + c0 + 4 * q;
-                if (md == kPipeDirect) {
-                    if (nx > 0 && my1 > my0) {
-                        const float *rowp = img + ((size_t)my0 * W + sl.xs[pw]) * (size_t)C;
-                        sweep_rows<0, PB, 1, NQ * 4>(rowp, (size_t)W * C, C, my0, my1, wxp, wyp, ys, ny, acc, nx);
-                    }
-                } else {
-                    const float *roi = rois + (size_t)k * 5;
-                    const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
-#pragma unroll 1
-                    for (int pi = 0; pi < PB; ++pi) {
-                        const int ph = ph0 + pi;
-                        float a[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int iy = 0; iy < g.gh; ++iy) {
-                            int yl, yh;
-                            float ly, hy;
-                            const bool oky = axis_sample(sample_coord(g.start_h, g.bin_h, ph, iy, g.gh), H, yl, yh, ly, hy);
-                            for (int ix = 0; ix < g.gw; ++ix) {
-                                int xl, xh;
-                                float lx, hx;
-                                const bool okx = axis_sample(sample_coord(g.start_w, g.bin_w, pw, ix, g.gw), W, xl, xh, lx, hx);
-                                if (!(oky && okx)) continue;
-                                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-                                const float4 v1 = ldg_f4(img + ((size_t)yl * W + xl) * C), v2 = ldg_f4(img + ((size_t)yl * W + xh) * C);
-                                const float4 v3 = ldg_f4(img + ((size_t)yh * W + xl) * C), v4 = ldg_f4(img + ((size_t)yh * W + xh) * C);
-                                a[0] += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-                                a[1] += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-                                a[2] += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-                                a[3] += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
-                            }
-                        }
-#pragma unroll
-                        for (int pp = 0; pp < PB; ++pp) {
-                            if (pp == pi) {
-                                acc[pp][0][0].x += __fdiv_rn(a[0], g.count);
-                                acc[pp][0][0].y += __fdiv_rn(a[1], g.count);
-                                acc[pp][0][1].x += __fdiv_rn(a[2], g.count);
-                                acc[pp][0][1].y += __fdiv_rn(a[3], g.count);
-                            }
-                        }
-                    }
-                }
-            }
-            // the slot can be rebuilt as soon as every consumer warp has its taps out of it
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
-        }
-
-        // ---- flush the unit: transpose into the tile (lane-rotated channel order: conflict-free), stream it out
+    // ---- flush: transpose the accumulators into the tile (lane-rotated channel order: conflict-free), stream it out
+    auto flush = [&](int k, int c0) {
         asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); // the previous flush has left the tile (thread 0 waited on its store)
         if (worker) {
 #pragma unroll
@@ -890,14 +825,143 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                 st_stream_f4(outp + 4 * i, make_float4(t[0], t[1], t[2], t[3]));
             }
         }
+    };
+    for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        int k = 0, c0 = 0;
+        for (int it = 0; it < nlev; ++it, ++itemctr) {
+            const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
+            mbar_wait(tfull0 + 8 * slot, use & 1);
+            const PipeSlot<P> &sl = s_slot[slot];
+            const int md = sl.mode, y0 = sl.y0, y1 = sl.y1, l = sl.level;
+            k = sl.k;
+            const int nx = sl.nx[pw];
+            int ys[PB], ny[PB];
+            int my0 = 1 << 30, my1 = -1;
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                ys[i] = sl.ys[ph0 + i];
+                ny[i] = sl.ny[ph0 + i];
+                if (ny[i] > 0) {
+                    my0 = min(my0, ys[i]);
+                    my1 = max(my1, ys[i] + ny[i]);
+                }
+            }
+            const float *wxp = sl.wx[pw], *wyp = sl.wy[ph0];
+            if (!worker) { my0 = 0; my1 = 0; }
+            for (int chunk = 0; chunk < nchunk; ++chunk) {
+                c0 = chunk * CC;
+                if (md == kPipeStaged) {
+                    if (y1 > y0) {
+                        const int xoff = sl.xs[pw] - sl.x0;
+                        if (nx <= 0) { my0 = 0; my1 = 0; } // no valid sample in this column: still take part in the row barriers
+                        const float *wyd = &sl.wyd[0][ph0 / 7 * 8];
+                        switch (nx) {
+                            case 1: staged_rows<1, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            case 2: staged_rows<2, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            case 3: staged_rows<3, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            case 4: staged_rows<4, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            default: staged_rows<0, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx > 0 ? nx : 0, my0, my1); break;
+                        }
+                    }
+                } else if (worker) {
+                    const int H = lv.H[l], W = lv.W[l];
+                    const float *img = lv.data[l] + (size_t)sl.batch * H * W * C + c0 + 4 * q;
+                    if (md == kPipeDirect) {
+                        if (nx > 0 && my1 > my0) {
+                            const float *rowp = img + ((size_t)my0 * W + sl.xs[pw]) * (size_t)C;
+                            sweep_rows<0, PB, 1, NQ * 4>(rowp, (size_t)W * C, C, my0, my1, wxp, wyp, ys, ny, acc, nx);
+                        }
+                    } else {
+                        const float *roi = rois + (size_t)k * 5;
+                        const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+    #pragma unroll 1
+                        for (int pi = 0; pi < PB; ++pi) {
+                            const int ph = ph0 + pi;
+                            float a[4] = {0.f, 0.f, 0.f, 0.f};
+                            for (int iy = 0; iy < g.gh; ++iy) {
+                                int yl, yh;
+                                float ly, hy;
+                                const bool oky = axis_sample(sample_coord(g.start_h, g.bin_h, ph, iy, g.gh), H, yl, yh, ly, hy);
+                                for (int ix = 0; ix < g.gw; ++ix) {
+                                    int xl, xh;
+                                    float lx, hx;
+                                    const bool okx = axis_sample(sample_coord(g.start_w, g.bin_w, pw, ix, g.gw), W, xl, xh, lx, hx);
+                                    if (!(oky && okx)) continue;
+                                    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                                    const float4 v1 = ldg_f4(img + ((size_t)yl * W + xl) * C), v2 = ldg_f4(img + ((size_t)yl * W + xh) * C);
+                                    const float4 v3 = ldg_f4(img + ((size_t)yh * W + xl) * C), v4 = ldg_f4(img + ((size_t)yh * W + xh) * C);
+                                    a[0] += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+                                    a[1] += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+                                    a[2] += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+                                    a[3] += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+                                }
+                            }
+    #pragma unroll
+                            for (int pp = 0; pp < PB; ++pp) {
+                                if (pp == pi) {
+                                    acc[pp][0][0].x += __fdiv_rn(a[0], g.count);
+                                    acc[pp][0][0].y += __fdiv_rn(a[1], g.count);
+                                    acc[pp][0][1].x += __fdiv_rn(a[2], g.count);
+                                    acc[pp][0][1].y += __fdiv_rn(a[3], g.count);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (nchunk > 1) flush(k, c0); // every channel chunk of the RoI is its own output tile
+            }
+            // the slot can be rebuilt as soon as every consumer warp has its taps out of it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
+        }
+
+        if (nchunk == 1) flush(k, 0);
     }
     if (kBulkStore && tid == 0) tma_store_wait_all(); // global writes complete before the CTA retires
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() { // resolved through the runtime: no link-time dependency on libcuda
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// maps of every level for a CTA that owns CC channels; false if the driver entry point is unavailable
+static bool build_tmaps(const RoiLevels &lv, int B, int C, int CC, RoiTmaps *tm) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || lv.L > kTmapLevels) return false;
+    for (int l = 0; l < lv.L; ++l)
+        for (int v = 0; v < kTmapBoxes; ++v) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)B * lv.H[l] * lv.W[l]};
+            const cuuint64_t gstride[1] = {(cuuint64_t)C * 4};
+            const cuuint32_t box[2] = {(cuuint32_t)CC, (cuuint32_t)tmap_box_px(v)};
+            const cuuint32_t estr[2] = {1, 1};
+            if (enc(&tm->m[l][v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)lv.data[l], gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return false;
+        }
+    return true;
+}
+
 template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
-static int launch_pipe(const RoiLevels &lv, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
+static int launch_pipe(const RoiLevels &lv, int B, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
                        float *out, cudaStream_t st) {
     static int grid_cached = 0;
+    static_assert(WMAX <= tmap_box_px(kTmapBoxes - 1) || true, "");
+    RoiTmaps tm;
+    memset(&tm, 0, sizeof tm);
+    if (C / (NQ * 4) > 1) {
+        if (WMAX > tmap_box_px(kTmapBoxes - 1) || !build_tmaps(lv, B, C, NQ * 4, &tm)) return 1; // caller falls back
+    }
     const size_t smem = sizeof(float) * ((size_t)NS * WMAX * NQ * 4 + NQ * 4 * SepCfg<P>::S) + kPipeSlots * sizeof(PipeSlot<P>) +
                         sizeof(uint64_t) * (2 * NS + 2 * kPipeSlots) + 128;
     auto kern = roi_align_pipe_kernel<P, NQ, PHS, NS, WMAX, MINB>;
@@ -912,10 +976,10 @@ static int launch_pipe(const RoiLevels &lv, int C, const float *rois, int K, int
         }
         grid_cached = per_sm * nuhtc_sm_count(); // persistent: every CTA resident, a multiple of the SM count
     }
-    const long nunits = (long)K * (C / (NQ * 4));
+    const long nunits = K;
     const int grid = (int)(nunits < grid_cached ? nunits : grid_cached);
     static const int bulk = getenv("NUHTC_RA_BULK") ? atoi(getenv("NUHTC_RA_BULK")) : 1;
-    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out, bulk);
+    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out, bulk, tm);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }
@@ -967,17 +1031,19 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
                          C % 64 == 0 && aligned16;
     if (fast_ok && ra_pipe()) {
         const int sr = sampling_ratio;
-        if (PH == 7) {
-            if (C == 256) {
-                static const int narrow = getenv("NUHTC_RA_NARROW") ? atoi(getenv("NUHTC_RA_NARROW")) : 0;
-                if (!narrow) return launch_pipe<7, 64, 1, 5, 32, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-                return launch_pipe<7, 64, 1, 9, 18, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-            }
-            if (C == 128) return launch_pipe<7, 32, 1, 8, 24, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-            if (C == 64) return launch_pipe<7, 16, 1, 8, 24, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-        } else if (C == 64) { // one bulk copy per window row needs the CTA to own every channel of the level
-            return launch_pipe<14, 16, 2, 8, 24, 1>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+        int rc = 1; // 1 = not handled by the pipelined kernel
+        if (PH == 7) { // the CTA owns every channel of the level: one plain bulk copy per window row
+            if (C == 256) rc = launch_pipe<7, 64, 1, 5, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            else if (C == 128) rc = launch_pipe<7, 32, 1, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            else if (C == 64) rc = launch_pipe<7, 16, 1, 8, 24, 2>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+        } else if (C == 64) {
+            rc = launch_pipe<14, 16, 2, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+        } else if ((mode == NUHTC_ROI_ROUTE || L == 1) && getenv("NUHTC_RA_TMAP")) {
+            // 64-channel chunks fetched through 2-D tensor maps (cp.async.bulk.tensor).  Correct, but measured slower than
+            // the non-pipelined kernel for 14x14 at C=256 (1.74 vs 1.52 ms at K=16000), so it is opt-in.
+            rc = launch_pipe<14, 16, 2, 12, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
         }
+        if (rc != 1) return rc;
     }
     if (fast_ok) {
         const int sr = sampling_ratio;
