@@ -62,10 +62,23 @@ int nuhtc_nchw_to_nhwc(const float *in, float *out, int B, int C, int H, int W, 
 #define NUHTC_ROI_SUM 1
 #define NUHTC_IMPL_AUTO 0
 #define NUHTC_IMPL_DIRECT 1
+/*   bias       NULL, or [K,C] fp32 added to every bin of (RoI k, channel c) after the level sum -- the broadcast
+ *              attention vector of AttentionRoIExtractor (roi_extractors_cus.py:238,246), fused into the store. */
 int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const int *W, const float *scale, int L,
                         int B, int C, int layout, const float *rois, int K, int PH, int PW,
                         int sampling_ratio, int aligned, int mode, float finest_scale, int impl, float *out,
-                        void *stream);
+                        const float *bias, void *stream);
+
+/* ---- cosine-attention pooling (AttentionRoIExtractor, levels >= start_level) ---------------------------------------
+ * Replaces nuhtc/models/roi_extractors_cus.py:220-238 for one level: for RoI k with centre cell
+ * (b, floor((y1+y2)/(2*stride)), floor((x1+x2)/(2*stride))) (clamped to the map),
+ *   out[k,:] (+)= mean_{h,w}( feat[b,:,h,w] * (relu(cos(feat[b,:,cy,cx], feat[b,:,h,w]) - thres) + thres) ).
+ *   feat_nhwc [B,H,W,C] fp32 (C <= 64), rois [K,5], out [K,C]; accumulate != 0 adds to out (second level).
+ *   status [1] int32: 2 = a RoI's batch index is outside [0,B). */
+size_t nuhtc_attention_pool_workspace_bytes(int K, int B);
+int nuhtc_attention_pool(const float *feat_nhwc, int B, int H, int W, int C, const float *rois, int K, float stride,
+                         float thres, int accumulate, float *out, int32_t *status, void *ws, size_t ws_bytes,
+                         void *stream);
 
 /* ---- NMS -----------------------------------------------------------------------------------
  * Replaces mmcv `ext_module.nms(boxes, scores, iou_threshold, offset)` and the class-offset

@@ -30,7 +30,9 @@ SIGNATURES = {
     "nuhtc_last_error": (_c.c_char_p, []),
     "nuhtc_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "nuhtc_roi_align_fwd": (_i, [_c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_f), _i, _i, _i, _i, _vp, _i,
-                                 _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+                                 _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "nuhtc_attention_pool_workspace_bytes": (_sz, [_i, _i]),
+    "nuhtc_attention_pool": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_nms_workspace_bytes": (_sz, [_i64, _i, _i64, _i]),
     "nuhtc_nms": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_paste_masks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
@@ -89,7 +91,7 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
 # ---- launch accounting: how many of OUR kernels each C-ABI call enqueues (bench.py reports the sum as
 # "gpu_launches"; library kernels such as cub's radix sort are not counted)
 LAUNCHES = {"n": 0}
-KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "roi_align": 1, "nms": 7, "paste": 2, "pack": 3, "mask_nms": 6, "merge": 16}
+KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "attention_pool": 4, "roi_align": 1, "nms": 7, "paste": 2, "pack": 3, "mask_nms": 6, "merge": 16}
 
 
 def count(op: str, n: int = 1) -> None:

@@ -126,7 +126,7 @@ __device__ __forceinline__ float direct_one(const float *plane, long sy, long sx
 
 __global__ void __launch_bounds__(256) roi_align_direct_kernel(RoiLevels lv, int C, int layout, const float *__restrict__ rois,
                                                                long total, int PH, int PW, int sr, int aligned, int mode,
-                                                               float finest, float *__restrict__ out) {
+                                                               float finest, float *__restrict__ out, const float *__restrict__ bias) {
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int pw = (int)(idx % PW);
         const int ph = (int)((idx / PW) % PH);
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) roi_align_direct_kernel(RoiLevels lv, int
             const float f = direct_one(plane, sy, sx, H, W, g, ph, pw);
             r = (mode == NUHTC_ROI_ROUTE) ? f : __fadd_rn(r, f);
         }
-        out[idx] = r;
+        out[idx] = bias ? __fadd_rn(r, __ldg(bias + k * C + c)) : r;
     }
 }
 
@@ -280,7 +280,7 @@ __device__ __forceinline__ void sweep_rows(const float *__restrict__ rowp, size_
 template <int P, int NQ, int PHS, int VEC, int MINB>
 __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int sr,
                                                                     int aligned, int mode, float finest,
-                                                                    float *__restrict__ out) {
+                                                                    float *__restrict__ out, const float *__restrict__ bias) {
     constexpr int CC = NQ * 4 * VEC;
     constexpr int PP = SepCfg<P>::PP;
     constexpr int S = SepCfg<P>::S;
@@ -420,7 +420,9 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
     for (int i = 0; i < PB; ++i) {
 #pragma unroll
         for (int u = 0; u < VEC; ++u) {
-            const float a0 = acc[i][u][0].x, a1 = acc[i][u][0].y, a2 = acc[i][u][1].x, a3 = acc[i][u][1].y;
+            float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) bz = ldg_f4(bias + (size_t)k * C + c0 + u * NQ * 4 + 4 * q);
+            const float a0 = acc[i][u][0].x + bz.x, a1 = acc[i][u][0].y + bz.y, a2 = acc[i][u][1].x + bz.z, a3 = acc[i][u][1].y + bz.w;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = (jj + rot) & 3;
@@ -460,7 +462,7 @@ static size_t sep_smem_bytes() {
 
 template <int P, int NQ, int PHS, int VEC, int MINB>
 static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
-                      float *out, cudaStream_t st) {
+                      float *out, const float *bias, cudaStream_t st) {
     static bool attr_done = false;
     const size_t smem = sep_smem_bytes<P, NQ, VEC>();
     if (!attr_done) {
@@ -468,7 +470,7 @@ static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int 
         attr_done = true;
     }
     dim3 grid(K, C / (NQ * 4 * VEC));
-    roi_align_sep_kernel<P, NQ, PHS, VEC, MINB><<<grid, NQ * P * PHS, smem, st>>>(lv, C, rois, sr, aligned, mode, finest, out);
+    roi_align_sep_kernel<P, NQ, PHS, VEC, MINB><<<grid, NQ * P * PHS, smem, st>>>(lv, C, rois, sr, aligned, mode, finest, out, bias);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }
@@ -614,7 +616,8 @@ __device__ __forceinline__ void staged_rows(const float *ring, int stage_floats,
 template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
 __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
     roi_align_pipe_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int K, int sr, int aligned, int mode, float finest,
-                          float *__restrict__ out, int bulk_store_flag, const __grid_constant__ RoiTmaps tm) {
+                          float *__restrict__ out, const float *__restrict__ bias, int bulk_store_flag,
+                          const __grid_constant__ RoiTmaps tm) {
     constexpr int CC = NQ * 4;
     constexpr int PP = SepCfg<P>::PP;
     const bool kBulkStore = (SepCfg<P>::S == PP) && bulk_store_flag != 0;            // contiguous tile == contiguous global chunk
@@ -789,8 +792,11 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
         asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); // the previous flush has left the tile (thread 0 waited on its store)
         if (worker) {
 #pragma unroll
+            float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) bz = ldg_f4(bias + (size_t)k * C + c0 + 4 * q);
+#pragma unroll
             for (int i = 0; i < PB; ++i) {
-                const float a0 = acc[i][0][0].x, a1 = acc[i][0][0].y, a2 = acc[i][0][1].x, a3 = acc[i][0][1].y;
+                const float a0 = acc[i][0][0].x + bz.x, a1 = acc[i][0][0].y + bz.y, a2 = acc[i][0][1].x + bz.z, a3 = acc[i][0][1].y + bz.w;
                 // rotate (a0..a3) left by rot with two conditional stages (the predicates are per-thread constants)
                 const float b0 = rot2 ? a2 : a0, b1 = rot2 ? a3 : a1, b2 = rot2 ? a0 : a2, b3 = rot2 ? a1 : a3;
                 s_tile[toff[0] + i * P] = rot1 ? b1 : b0;
@@ -954,7 +960,7 @@ static bool build_tmaps(const RoiLevels &lv, int B, int C, int CC, RoiTmaps *tm)
 
 template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
 static int launch_pipe(const RoiLevels &lv, int B, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
-                       float *out, cudaStream_t st) {
+                       float *out, const float *bias, cudaStream_t st) {
     static int grid_cached = 0;
     static_assert(WMAX <= tmap_box_px(kTmapBoxes - 1) || true, "");
     RoiTmaps tm;
@@ -979,7 +985,7 @@ static int launch_pipe(const RoiLevels &lv, int B, int C, const float *rois, int
     const long nunits = K;
     const int grid = (int)(nunits < grid_cached ? nunits : grid_cached);
     static const int bulk = getenv("NUHTC_RA_BULK") ? atoi(getenv("NUHTC_RA_BULK")) : 1;
-    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out, bulk, tm);
+    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, bulk, tm);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }
@@ -1005,7 +1011,8 @@ static int ra_vec() {
 
 NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const int *W, const float *scale, int L, int B,
                                   int C, int layout, const float *rois, int K, int PH, int PW, int sampling_ratio,
-                                  int aligned, int mode, float finest_scale, int impl, float *out, void *stream) {
+                                  int aligned, int mode, float finest_scale, int impl, float *out, const float *bias,
+                                  void *stream) {
     NUHTC_CHECK_ARG(L >= 1 && L <= NUHTC_MAX_LEVELS, "roi_align: L=%d out of range", L);
     NUHTC_CHECK_ARG(B >= 0 && C >= 1 && PH >= 1 && PW >= 1 && K >= 0, "roi_align: bad sizes B=%d C=%d PH=%d PW=%d K=%d", B, C,
                     PH, PW, K);
@@ -1033,15 +1040,15 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
         const int sr = sampling_ratio;
         int rc = 1; // 1 = not handled by the pipelined kernel
         if (PH == 7) { // the CTA owns every channel of the level: one plain bulk copy per window row
-            if (C == 256) rc = launch_pipe<7, 64, 1, 5, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-            else if (C == 128) rc = launch_pipe<7, 32, 1, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-            else if (C == 64) rc = launch_pipe<7, 16, 1, 8, 24, 2>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            if (C == 256) rc = launch_pipe<7, 64, 1, 5, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+            else if (C == 128) rc = launch_pipe<7, 32, 1, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+            else if (C == 64) rc = launch_pipe<7, 16, 1, 8, 24, 2>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         } else if (C == 64) {
-            rc = launch_pipe<14, 16, 2, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            rc = launch_pipe<14, 16, 2, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         } else if ((mode == NUHTC_ROI_ROUTE || L == 1) && getenv("NUHTC_RA_TMAP")) {
             // 64-channel chunks fetched through 2-D tensor maps (cp.async.bulk.tensor).  Correct, but measured slower than
             // the non-pipelined kernel for 14x14 at C=256 (1.74 vs 1.52 ms at K=16000), so it is opt-in.
-            rc = launch_pipe<14, 16, 2, 12, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            rc = launch_pipe<14, 16, 2, 12, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         }
         if (rc != 1) return rc;
     }
@@ -1050,18 +1057,18 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
         const bool v2 = ra_vec() >= 2;
         if (PH == 7) {
             if (C % 256 == 0) {
-                if (ra_vec() == 3) return launch_sep<7, 32, 1, 2, 3>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-                if (v2) return launch_sep<7, 32, 1, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-                return launch_sep<7, 64, 1, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+                if (ra_vec() == 3) return launch_sep<7, 32, 1, 2, 3>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+                if (v2) return launch_sep<7, 32, 1, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+                return launch_sep<7, 64, 1, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
             }
             if (C % 128 == 0) {
-                if (v2) return launch_sep<7, 16, 1, 2, 4>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-                return launch_sep<7, 32, 1, 1, 4>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+                if (v2) return launch_sep<7, 16, 1, 2, 4>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+                return launch_sep<7, 32, 1, 1, 4>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
             }
-            return launch_sep<7, 16, 1, 1, 8>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+            return launch_sep<7, 16, 1, 1, 8>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         }
-        if (v2) return launch_sep<14, 8, 2, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
-        return launch_sep<14, 16, 2, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, st);
+        if (v2) return launch_sep<14, 8, 2, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+        return launch_sep<14, 16, 2, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
     }
     const long total = (long)K * C * PH * PW;
     const int threads = 256;
@@ -1069,7 +1076,7 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
     const long cap = (long)nuhtc_sm_count() * 32;
     if (blocks > cap) blocks = cap;
     roi_align_direct_kernel<<<(unsigned)blocks, threads, 0, st>>>(lv, C, layout, rois, total, PH, PW, sampling_ratio, aligned,
-                                                                  mode, finest_scale, out);
+                                                                  mode, finest_scale, out, bias);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }

@@ -22,7 +22,7 @@ import torch.nn as nn
 from . import _lib as L
 
 __all__ = ["RoIAlign", "roi_align", "nms", "batched_nms", "roi_align_levels", "to_nhwc", "clear_layout_cache",
-           "nms_groups"]
+           "nms_groups", "attention_pool"]
 
 
 def _pair(x) -> Tuple[int, int]:
@@ -74,7 +74,7 @@ def _fast_path_ok(C: int, ph: int, pw: int) -> bool:
 
 def roi_align_levels(feats: Sequence[torch.Tensor], rois: torch.Tensor, output_size, spatial_scales: Sequence[float],
                      sampling_ratio: int = 0, aligned: bool = True, mode: str = "route", finest_scale: float = 56.0,
-                     impl: str = "auto", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     impl: str = "auto", out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """All FPN levels in ONE launch.
 
     mode 'route': each RoI is pooled on the level SingleRoIExtractor.map_roi_levels picks
@@ -97,6 +97,9 @@ def roi_align_levels(feats: Sequence[torch.Tensor], rois: torch.Tensor, output_s
         assert out.shape == (K, C, ph, pw) and out.is_contiguous() and out.dtype == torch.float32
     if K == 0:
         return out
+    if bias is not None:
+        assert bias.shape == (K, C) and bias.dtype == torch.float32 and bias.is_cuda
+        bias = bias.contiguous()
     use_fast = impl == "auto" and _fast_path_ok(C, ph, pw)
     bufs = []
     for f in feats:
@@ -115,9 +118,38 @@ def roi_align_levels(feats: Sequence[torch.Tensor], rois: torch.Tensor, output_s
     with torch.cuda.device(dev):
         rc = L.lib().nuhtc_roi_align_fwd(ptrs, Hs, Ws, sc, nl, B, C, layout, rois.data_ptr(), K, ph, pw, int(sampling_ratio),
                                          int(bool(aligned)), m, float(finest_scale),
-                                         L.IMPL_AUTO if use_fast else L.IMPL_DIRECT, out.data_ptr(), L.stream_ptr(dev))
+                                         L.IMPL_AUTO if use_fast else L.IMPL_DIRECT, out.data_ptr(), L.ptr(bias),
+                                         L.stream_ptr(dev))
     L.check(rc, "roi_align_fwd")
     L.count("roi_align")
+    return out
+
+
+def attention_pool(feat: torch.Tensor, rois: torch.Tensor, stride: float, thres: float = 0.0,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Cosine-attention global pooling of one level (AttentionRoIExtractor, roi_extractors_cus.py:220-238):
+    feat [B,C,H,W] fp32 CUDA (C <= 64), rois [K,5] -> [K,C]; with ``out`` given the result is ADDED to it."""
+    L.require_cuda(feat, "feat")
+    L.require_cuda(rois, "rois")
+    B, C, H, W = feat.shape
+    K = rois.shape[0]
+    dev = feat.device
+    nhwc = to_nhwc(feat)
+    rois = rois.to(torch.float32).contiguous()
+    acc = out is not None
+    if out is None:
+        out = torch.empty((K, C), dtype=torch.float32, device=dev)
+    if K == 0:
+        return out
+    lib = L.lib()
+    wsb = lib.nuhtc_attention_pool_workspace_bytes(K, B)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.nuhtc_attention_pool(nhwc.data_ptr(), B, H, W, C, rois.data_ptr(), K, float(stride), float(thres), int(acc),
+                                      out.data_ptr(), status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev))
+    L.check(rc, "attention_pool")
+    L.count("attention_pool")
     return out
 
 

@@ -146,6 +146,35 @@ def sum_roi_extract(feats: Sequence[torch.Tensor], rois: torch.Tensor, featmap_s
     return out
 
 
+def attention_roi_extract(feats: Sequence[torch.Tensor], rois: torch.Tensor, featmap_strides: Sequence[int], output_size: int,
+                          sampling_ratio: int, start_level: int = 2, thres: float = 0.0, nthreads: int = 1) -> torch.Tensor:
+    """AttentionRoIExtractor.forward, aggregation='sum' (nuhtc/models/roi_extractors_cus.py:195-259), fp32 CPU branch:
+    levels < start_level -> RoIAlign on every RoI; levels >= start_level -> cosine-attention pooled vector of the RoI's
+    centre cell, broadcast over the bins; all summed in level order."""
+    K, C = rois.shape[0], feats[0].shape[1]
+    out = torch.zeros(K, C, output_size, output_size)
+    if K == 0:
+        return out
+    for i, f in enumerate(feats):
+        if i < start_level:
+            t = roi_align(f, rois, output_size, 1.0 / featmap_strides[i], sampling_ratio, nthreads=nthreads)
+        else:
+            B, _, H, W = f.shape
+            sf = 4 * 2 ** i
+            rx = torch.div(rois[:, 1] + rois[:, 3], 2 * sf, rounding_mode="floor").clamp(0, W - 1)
+            ry = torch.div(rois[:, 2] + rois[:, 4], 2 * sf, rounding_mode="floor").clamp(0, H - 1)
+            loc = torch.stack((rois[:, 0], ry, rx), dim=1)
+            uni, inv = loc.unique(dim=0, return_inverse=True)
+            uni = uni.long()
+            vec = f[uni[:, 0], :, uni[:, 1], uni[:, 2]]
+            pos = f[uni[:, 0]].permute(0, 2, 3, 1).reshape(-1, H * W, C)
+            sim = F.relu(F.cosine_similarity(vec.unsqueeze(1), pos, dim=2) - thres) + thres
+            pooled = torch.mean(f[uni[:, 0]] * sim.view(-1, 1, H, W), dim=(2, 3))
+            t = pooled[inv][:, :, None, None].expand(K, C, output_size, output_size)
+        out = out + t
+    return out
+
+
 # --------------------------------------------------------------------------- NMS
 def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
     """mmcv.ops.nms (Python wrapper + nms_cpu).  Returns (dets [k,5], inds [k] int64)."""

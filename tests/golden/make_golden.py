@@ -99,6 +99,29 @@ def main():
     dets, labels, _ = mc(bx, sc, 0.35, dict(type="nms", iou_threshold=0.5), 500, return_inds=True)
     np.savez_compressed(os.path.join(HERE, "multiclass_nms.npz"), boxes=bx.numpy(), scores=sc.numpy(), dets=dets.numpy(),
                         labels=labels.numpy())
+    # ---- AttentionRoIExtractor.forward (the extractor of all four shipped configs) with mmcv's RoIAlign layers
+    # replaced by the oracle's restatement: pins the attention branch, the centre-cell rule and the level sum
+    import einops
+
+    class _Layer:
+        def __init__(self, scale, P, sr):
+            self.output_size, self.scale, self.sr = (P, P), scale, sr
+
+        def __call__(self, feat, r):
+            return O.roi_align(feat, r, self.output_size[0], self.scale, self.sr)
+
+    class _Ext:
+        out_channels, start_level, thres, aggregation, with_pre, with_post = 64, [2, 3], 0, "sum", False, False
+        roi_layers = [_Layer(1 / s_, 7, 2) for s_ in (4, 8, 16, 32)]
+
+        def roi_rescale(self, r, f):
+            raise NotImplementedError
+
+    att = extract("nuhtc/models/roi_extractors_cus.py", "forward", cls="AttentionRoIExtractor", extra={"einops": einops})
+    feats = synth.fpn_levels(2, 64, frame=256, seed=21)
+    arois = synth.proposals(2, 60, "nuclei", frame=256, seed=22)
+    aout = att(_Ext(), feats, arois)
+    np.savez_compressed(os.path.join(HERE, "attention_extractor.npz"), rois=arois.numpy(), out=aout.numpy())
     print("golden vectors written to", HERE)
 
 

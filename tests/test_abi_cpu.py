@@ -65,7 +65,7 @@ def test_argument_validation_without_gpu():
     """bad arguments are rejected by the library before any CUDA call"""
     from nuhtc_b200 import _lib
     L = _lib.lib()
-    assert L.nuhtc_roi_align_fwd(None, None, None, None, 0, 1, 64, 1, None, 1, 7, 7, 0, 1, 0, 56.0, 0, None, None) == -1
+    assert L.nuhtc_roi_align_fwd(None, None, None, None, 0, 1, 64, 1, None, 1, 7, 7, 0, 1, 0, 56.0, 0, None, None, None) == -1
     assert b"L=0" in L.nuhtc_last_error()
     assert L.nuhtc_paste_masks(None, None, 1, 100, 100, 8, 8, 0.5, 1, None, None, None, None) == -1
     assert L.nuhtc_nms_workspace_bytes(5000, 16, 5000, 0) > 5000 * 79 * 8

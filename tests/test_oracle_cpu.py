@@ -236,3 +236,11 @@ def test_merge_oracle_equals_naive_greedy(oracle):
     assert got.tolist() == kept
     area = oracle.merge_overlap_arrays(d["xy"], d["voff"], d["score"], 0.05, "area")
     assert len(area) == len(kept) and set(area.tolist()) != set(kept)
+
+
+def test_golden_attention_extractor(oracle):
+    """AttentionRoIExtractor.forward executed from the reference source (mmcv RoIAlign layers -> oracle) vs the restatement."""
+    z = np.load(os.path.join(G, "attention_extractor.npz"))
+    feats = synth.fpn_levels(2, 64, frame=256, seed=21)
+    out = oracle.attention_roi_extract(feats, torch.from_numpy(z["rois"]), (4, 8, 16, 32), 7, 2, start_level=2, thres=0.0)
+    assert torch.equal(out, torch.from_numpy(z["out"]))
