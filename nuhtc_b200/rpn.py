@@ -1,0 +1,121 @@
+"""RPN proposal post-processing: per-level top-k, delta2bbox, batched NMS with the level id as the
+label, top ``max_per_img`` -- same flow as RPNHead._get_bboxes_single / _bbox_post_process
+(/root/reference/thirdparty/mmdetection/mmdet/models/dense_heads/rpn_head.py:103-236), on the B200 NMS kernels.
+
+``get_bboxes_single`` / ``bbox_post_process`` keep the reference's per-image semantics; ``proposals_batched`` runs all
+images of a batch through ONE grouped NMS launch (image = group, level = class segment).
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Sequence
+
+import torch
+
+from .mmcv_ops import batched_nms, nms_groups
+from .roi_stage import delta2bbox
+
+__all__ = ["get_bboxes_single", "bbox_post_process", "proposals_batched"]
+
+
+def _cfg_get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def _level_topk(cls_score: torch.Tensor, bbox_pred: torch.Tensor, anchors: torch.Tensor, nms_pre: int, use_sigmoid_cls: bool):
+    assert cls_score.size()[-2:] == bbox_pred.size()[-2:]
+    cls_score = cls_score.permute(1, 2, 0)
+    if use_sigmoid_cls:
+        scores = cls_score.reshape(-1).sigmoid()
+    else:
+        scores = cls_score.reshape(-1, 2).softmax(dim=1)[:, 0]
+    bbox_pred = bbox_pred.permute(1, 2, 0).reshape(-1, 4)
+    if 0 < nms_pre < scores.shape[0]:
+        ranked_scores, rank_inds = scores.sort(descending=True)
+        topk_inds = rank_inds[:nms_pre]
+        scores = ranked_scores[:nms_pre]
+        bbox_pred = bbox_pred[topk_inds, :]
+        anchors = anchors[topk_inds, :]
+    return scores, bbox_pred, anchors
+
+
+def bbox_post_process(mlvl_scores, mlvl_bboxes, mlvl_valid_anchors, level_ids, cfg, img_shape):
+    """RPNHead._bbox_post_process (rpn_head.py:189-236): returns dets [n,5]."""
+    scores = torch.cat(mlvl_scores)
+    anchors = torch.cat(mlvl_valid_anchors)
+    rpn_bbox_pred = torch.cat(mlvl_bboxes)
+    proposals = delta2bbox(anchors, rpn_bbox_pred, (1., 1., 1., 1.), max_shape=img_shape)
+    ids = torch.cat(level_ids)
+    min_bbox_size = _cfg_get(cfg, "min_bbox_size", -1)
+    if min_bbox_size >= 0:
+        w = proposals[:, 2] - proposals[:, 0]
+        h = proposals[:, 3] - proposals[:, 1]
+        valid_mask = (w > min_bbox_size) & (h > min_bbox_size)
+        if not valid_mask.all():
+            proposals, scores, ids = proposals[valid_mask], scores[valid_mask], ids[valid_mask]
+    if proposals.numel() > 0:
+        dets, _ = batched_nms(proposals, scores, ids, _cfg_get(cfg, "nms"))
+    else:
+        return proposals.new_zeros(0, 5)
+    return dets[:_cfg_get(cfg, "max_per_img")]
+
+
+def get_bboxes_single(cls_score_list: Sequence[torch.Tensor], bbox_pred_list: Sequence[torch.Tensor],
+                      mlvl_anchors: Sequence[torch.Tensor], img_shape, cfg, use_sigmoid_cls: bool = True):
+    """RPNHead._get_bboxes_single (rpn_head.py:103-187) for one image."""
+    cfg = copy.deepcopy(cfg)
+    nms_pre = _cfg_get(cfg, "nms_pre", -1)
+    level_ids, mlvl_scores, mlvl_bbox_preds, mlvl_valid_anchors = [], [], [], []
+    for level_idx in range(len(cls_score_list)):
+        scores, bbox_pred, anchors = _level_topk(cls_score_list[level_idx], bbox_pred_list[level_idx], mlvl_anchors[level_idx],
+                                                 nms_pre, use_sigmoid_cls)
+        mlvl_scores.append(scores)
+        mlvl_bbox_preds.append(bbox_pred)
+        mlvl_valid_anchors.append(anchors)
+        level_ids.append(scores.new_full((scores.size(0),), level_idx, dtype=torch.long))
+    return bbox_post_process(mlvl_scores, mlvl_bbox_preds, mlvl_valid_anchors, level_ids, cfg, img_shape)
+
+
+@torch.no_grad()
+def proposals_batched(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[torch.Tensor], mlvl_anchors: Sequence[torch.Tensor],
+                      img_shape, cfg, use_sigmoid_cls: bool = True) -> List[torch.Tensor]:
+    """All B images at once: ``cls_scores[l]`` is [B, A(*2), H_l, W_l], ``bbox_preds[l]`` [B, A*4, H_l, W_l].
+    Same result per image as ``get_bboxes_single`` (below mmcv's split_thr the NMS runs on offset boxes; decoded boxes are
+    clamped to the frame, so the level segments are exact), one NMS launch for the batch."""
+    B = cls_scores[0].shape[0]
+    nms_cfg = dict(_cfg_get(cfg, "nms"))
+    assert nms_cfg.pop("type", "nms") == "nms"
+    iou_thr = nms_cfg.pop("iou_threshold")
+    nms_pre = _cfg_get(cfg, "nms_pre", -1)
+    max_per_img = _cfg_get(cfg, "max_per_img")
+    min_bbox_size = _cfg_get(cfg, "min_bbox_size", -1)
+    L = len(cls_scores)
+    boxes, scores, labels, groups = [], [], [], []
+    per_image = 0
+    for b in range(B):
+        n_b = 0
+        for l in range(L):
+            s, d, a = _level_topk(cls_scores[l][b], bbox_preds[l][b], mlvl_anchors[l], nms_pre, use_sigmoid_cls)
+            boxes.append(delta2bbox(a, d, (1., 1., 1., 1.), max_shape=img_shape))
+            scores.append(s)
+            labels.append(s.new_full((s.numel(),), l, dtype=torch.long))
+            groups.append(torch.full((s.numel(),), b, dtype=torch.int32, device=s.device))
+            n_b += s.numel()
+        per_image = max(per_image, n_b)
+    boxes, scores, labels, groups = torch.cat(boxes), torch.cat(scores), torch.cat(labels), torch.cat(groups)
+    if min_bbox_size >= 0:
+        ok = ((boxes[:, 2] - boxes[:, 0]) > min_bbox_size) & ((boxes[:, 3] - boxes[:, 1]) > min_bbox_size)
+        groups = torch.where(ok, groups, torch.full_like(groups, -1))
+    split_thr = nms_cfg.pop("split_thr", 10000)
+    mode = "offset" if per_image < split_thr else "perclass"  # NB: mmcv decides on the per-image candidate count AFTER the size filter
+    keep, gstart, gcount, status = nms_groups(boxes, scores, labels, groups, B, per_image, iou_thr, 0, mode, num_classes=L)
+    host = torch.stack([gstart, torch.clamp(gcount, max=max_per_img)]).cpu()
+    if int(status.item()) != 0:
+        raise RuntimeError(f"rpn nms status {int(status.item())}")
+    out = []
+    for b in range(B):
+        k = keep[int(host[0, b]): int(host[0, b]) + int(host[1, b])]
+        out.append(torch.cat([boxes[k], scores[k, None]], dim=1))
+    return out

@@ -275,6 +275,21 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1):
     return dets, labels[keep], inds[keep]
 
 
+def rpn_bbox_post_process(scores, rpn_bbox_pred, anchors, ids, img_shape, nms_cfg, max_per_img, min_bbox_size=0):
+    """RPNHead._bbox_post_process (mmdet/models/dense_heads/rpn_head.py:189-236) on concatenated level tensors."""
+    proposals = delta2bbox(anchors, rpn_bbox_pred, max_shape=img_shape)
+    if min_bbox_size >= 0:
+        w = proposals[:, 2] - proposals[:, 0]
+        h = proposals[:, 3] - proposals[:, 1]
+        valid = (w > min_bbox_size) & (h > min_bbox_size)
+        if not valid.all():
+            proposals, scores, ids = proposals[valid], scores[valid], ids[valid]
+    if proposals.numel() == 0:
+        return proposals.new_zeros(0, 5)
+    dets, _ = batched_nms(proposals, scores, ids, nms_cfg)
+    return dets[:max_per_img]
+
+
 # --------------------------------------------------------------------------- paste
 def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int) -> torch.Tensor:
     """_do_paste_mask(..., skip_empty=False) (mmdet/.../fcn_mask_head.py:344-412): torch CPU grid_sample on the

@@ -122,6 +122,34 @@ def main():
     arois = synth.proposals(2, 60, "nuclei", frame=256, seed=22)
     aout = att(_Ext(), feats, arois)
     np.savez_compressed(os.path.join(HERE, "attention_extractor.npz"), rois=arois.numpy(), out=aout.numpy())
+    # ---- RPNHead._bbox_post_process from the reference source (bbox_coder.decode = the reference delta2bbox,
+    # batched_nms = the oracle's mmcv restatement)
+    class _Coder:
+        @staticmethod
+        def decode(anchors, deltas, max_shape=None):
+            return d2b(anchors, deltas, max_shape=max_shape)
+
+    class _Rpn:
+        bbox_coder = _Coder()
+
+    class _Cfg(dict):
+        __getattr__ = dict.get
+
+    post = extract("thirdparty/mmdetection/mmdet/models/dense_heads/rpn_head.py", "_bbox_post_process", cls="RPNHead",
+                   extra={"batched_nms": O.batched_nms})
+    n_lv = [600, 300, 150, 75]
+    anchors, deltas, sc, ids = [], [], [], []
+    for l, n_ in enumerate(n_lv):
+        ctr = torch.rand(n_, 2, generator=g) * 512
+        wh = (8 * 2 ** l) * (0.5 + torch.rand(n_, 2, generator=g))
+        anchors.append(torch.cat([ctr - wh / 2, ctr + wh / 2], 1))
+        deltas.append(torch.randn(n_, 4, generator=g) * 0.3)
+        sc.append(torch.rand(n_, generator=g))
+        ids.append(torch.full((n_,), l, dtype=torch.long))
+    rcfg = _Cfg(min_bbox_size=0, nms=dict(type="nms", iou_threshold=0.7), max_per_img=300)
+    rdets = post(_Rpn(), sc, deltas, anchors, ids, rcfg, (512, 512, 3))
+    np.savez_compressed(os.path.join(HERE, "rpn_post.npz"), anchors=torch.cat(anchors).numpy(), deltas=torch.cat(deltas).numpy(),
+                        scores=torch.cat(sc).numpy(), ids=torch.cat(ids).numpy(), dets=rdets.numpy())
     print("golden vectors written to", HERE)
 
 

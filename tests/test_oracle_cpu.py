@@ -244,3 +244,12 @@ def test_golden_attention_extractor(oracle):
     feats = synth.fpn_levels(2, 64, frame=256, seed=21)
     out = oracle.attention_roi_extract(feats, torch.from_numpy(z["rois"]), (4, 8, 16, 32), 7, 2, start_level=2, thres=0.0)
     assert torch.equal(out, torch.from_numpy(z["out"]))
+
+
+def test_rpn_post_process_golden(oracle):
+    """RPNHead._bbox_post_process (rpn_head.py:189-236): golden made by executing the reference method."""
+    z = np.load(os.path.join(G, "rpn_post.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    d = oracle.rpn_bbox_post_process(t("scores"), t("deltas"), t("anchors"), t("ids"), (512, 512, 3),
+                                     dict(type="nms", iou_threshold=0.7), 300)
+    assert torch.equal(d, t("dets"))
