@@ -185,6 +185,24 @@ int nuhtc_merge_graph(const double *xy, const int64_t *voff, const double *score
 int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_t *in_list, int64_t N,
                        const uint8_t *frozen, uint8_t *state, int64_t *remaining, int rounds, void *stream);
 
+/* ---- mask -> contour (tile post-processing) --------------------------------------
+ * Replaces `mask2inst` (tools/infer_wsi.py:51-54): cv2.findContours(mask, cv2.RETR_TREE,
+ * cv2.CHAIN_APPROX_SIMPLE)[0][0], called per nucleus at infer_wsi.py:528-529 after a device->host
+ * copy of every dense mask.  Suzuki-Abe border following on the bit rows; contour [0] of the tree
+ * is the last outer border in raster order whose parent is the frame.
+ *   bits [n,h,ceil(w/64)] uint64 (nuhtc_paste_masks BITS kind / nuhtc_pack_masks), device.
+ *   out_xy [n,max_pts,2] int32 (x,y) in mask coordinates, out_count [n] int32: the contour's
+ *   point count (0 for an empty mask).  A count above max_pts means the points were truncated.
+ *   status [1] int32: 0 ok, 1 some contour longer than max_pts, 2 a mask wider/taller than 64 px
+ *   whose frame does not fit shared memory (frames up to ~400x400 do).
+ * nuhtc_contour_rings: closed rings for nuhtc_merge: for every mask m with voff[m+1]-voff[m] = k > 0
+ *   writes k vertices (contour points, then its first point again: infer_wsi.py:53) + origin[m]
+ *   (tile coordinate, infer_wsi.py:531; NULL = 0) as fp64 at out[voff[m]..); k = 0 skips the mask. */
+int nuhtc_mask_contours(const uint64_t *bits, int64_t n, int h, int w, int max_pts, int32_t *out_xy,
+                        int32_t *out_count, int32_t *status, void *stream);
+int nuhtc_contour_rings(const int32_t *xy, const int32_t *count, const int64_t *voff, const int32_t *origin,
+                        int64_t n, int max_pts, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ from .mmcv_ops import RoIAlign, roi_align, nms, batched_nms, roi_align_levels, n
 from .mask_paste import _do_paste_mask, paste_masks, get_seg_masks, get_seg_masks_device
 from .mask_nms import mask_nms, mask_nms_device, pack_masks
 from .nuclei_merge import merge_arrays, merge_overlap
-from . import slide, synth, roi_stage
+from .contours import mask_contours, mask2inst, rings_for_merge
+from . import slide, synth, roi_stage, rpn, contours
 
 __version__ = "0.1.0"

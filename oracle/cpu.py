@@ -61,6 +61,7 @@ def lib():
         L.oracle_merge.argtypes = [c_dp, c_i64p, c_dp, ctypes.c_int64, ctypes.c_double, ctypes.c_int, c_i64p]
         L.oracle_merge.restype = ctypes.c_int64
         L.oracle_paste.argtypes = [c_fp, c_fp] + [ctypes.c_int] * 5 + [c_fp, ctypes.c_int]
+        L.oracle_contour0.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int]
         _lib = L
     return _lib
 
@@ -288,6 +289,22 @@ def rpn_bbox_post_process(scores, rpn_bbox_pred, anchors, ids, img_shape, nms_cf
         return proposals.new_zeros(0, 5)
     dets, _ = batched_nms(proposals, scores, ids, nms_cfg)
     return dets[:max_per_img]
+
+
+def contour0(mask: np.ndarray, approx_simple: bool = True) -> np.ndarray:
+    """cv2.findContours(mask, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0] as [n,2] int32 (x, y); empty mask -> [0,2]."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    h, w = m.shape
+    cap = 2 * h * w + 8
+    out = np.empty((cap, 2), dtype=np.int32)
+    n = lib().oracle_contour0(_u8p(m), h, w, int(approx_simple), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), cap)
+    return out[:n].copy()
+
+
+def mask2inst(inst_map: np.ndarray) -> np.ndarray:
+    """tools/infer_wsi.py:51-54: the first contour, closed by repeating its first point, shape [n+1,1,2]."""
+    c = contour0(inst_map).reshape(-1, 1, 2)
+    return np.concatenate([c, c[[0]]], axis=0)
 
 
 # --------------------------------------------------------------------------- paste

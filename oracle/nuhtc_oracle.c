@@ -551,3 +551,93 @@ API int oracle_paste(const float *probs, const float *boxes, int N, int mh, int 
 }
 
 API int oracle_abi_version(void) { return 1; }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * mask2inst (/root/reference/tools/infer_wsi.py:51-54): cv2.findContours(mask, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0].
+ * OpenCV (opencv-python, requirements.txt; not vendored) implements Suzuki & Abe 1985 "Topological structural analysis
+ * of digitized binary images by border following"; this is a restatement of that published algorithm with explicit
+ * border ids and parents:
+ *   - raster scan, LNBD = last border met on the row; outer border starts at f==1 with a 0 on its left, hole border at
+ *     f>=1 with a 0 on its right; parent from the (type of new border, type of LNBD) table of the paper;
+ *   - border following: clockwise search for the first neighbour, then counter-clockwise sweeps; a pixel whose right
+ *     neighbour was examined as 0 gets -NBD, otherwise NBD if still 1;
+ *   - CHAIN_APPROX_SIMPLE keeps a border point only where the chain direction changes;
+ *   - OpenCV returns the tree in pre-order with siblings in reverse order of discovery, so contour [0] is the LAST
+ *     outer border found whose parent is the frame.
+ * Pinned against cv2 itself (tests/golden/contours.npz made with cv2 4.13 here; live comparison when cv2 imports).
+ * Returns the number of points of contour [0] (0 for an empty mask); writes at most cap (x, y) pairs. */
+static const int C_DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+static const int C_DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+API int oracle_contour0(const uint8_t *mask, int h, int w, int approx_simple, int32_t *out_xy, int cap) {
+    const int W2 = w + 2;
+    int32_t *f = (int32_t *)calloc((size_t)(h + 2) * W2, sizeof(int32_t));
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) f[(y + 1) * W2 + x + 1] = mask[(size_t)y * w + x] ? 1 : 0;
+    int nb_cap = 64, nbd = 1;
+    uint8_t *is_hole = (uint8_t *)malloc(nb_cap);
+    int32_t *parent = (int32_t *)malloc(sizeof(int32_t) * nb_cap);
+    is_hole[1] = 1; parent[1] = 0;                   /* the frame acts as a hole border */
+    int best_i = -1, best_j = -1;                    /* start of the last outer border whose parent is the frame */
+    for (int i = 1; i <= h; ++i) {
+        int lnbd = 1;
+        for (int j = 1; j <= w; ++j) {
+            int32_t *p0 = f + i * W2 + j;
+            if (*p0 == 0) continue;
+            int hole = -1;
+            if (*p0 == 1 && p0[-1] == 0) hole = 0;
+            else if (*p0 >= 1 && p0[1] == 0) { hole = 1; if (*p0 > 1) lnbd = *p0; }
+            if (hole >= 0) {
+                ++nbd;
+                if (nbd >= nb_cap) {
+                    nb_cap *= 2;
+                    is_hole = (uint8_t *)realloc(is_hole, nb_cap);
+                    parent = (int32_t *)realloc(parent, sizeof(int32_t) * nb_cap);
+                }
+                is_hole[nbd] = (uint8_t)hole;
+                parent[nbd] = (is_hole[lnbd] == hole) ? parent[lnbd] : lnbd;
+                if (!hole && parent[nbd] == 1) { best_i = i; best_j = j; }
+                /* follow the border */
+                int s_end = hole ? 0 : 4, s = s_end;
+                int32_t *i1;
+                do { s = (s - 1) & 7; i1 = p0 + C_DY[s] * W2 + C_DX[s]; } while (*i1 == 0 && s != s_end);
+                if (s == s_end) *p0 = -nbd;
+                else {
+                    int32_t *i3 = p0, *i4;
+                    for (;;) {
+                        s_end = s;
+                        for (;;) { ++s; i4 = i3 + C_DY[s & 7] * W2 + C_DX[s & 7]; if (*i4 != 0) break; }
+                        if (s > 8 && s_end < 8) *i3 = -nbd;        /* direction 0 (right) was examined as a 0-pixel */
+                        else if (*i3 == 1) *i3 = nbd;
+                        if (i4 == p0 && i3 == i1) break;
+                        i3 = i4; s = (s + 4) & 7;
+                    }
+                }
+            }
+            if (*p0 != 1) lnbd = *p0 < 0 ? -*p0 : *p0;
+        }
+    }
+    int n = 0;
+    if (best_i >= 0) {                               /* re-trace the chosen border and emit its points */
+        for (size_t k = 0; k < (size_t)(h + 2) * W2; ++k) f[k] = f[k] != 0;
+        int32_t *p0 = f + best_i * W2 + best_j, *i1;
+        int s_end = 4, s = 4, x = best_j - 1, y = best_i - 1;
+        do { s = (s - 1) & 7; i1 = p0 + C_DY[s] * W2 + C_DX[s]; } while (*i1 == 0 && s != s_end);
+        if (s == s_end) { if (n < cap) { out_xy[0] = x; out_xy[1] = y; } n = 1; }
+        else {
+            int32_t *i3 = p0, *i4;
+            int prev_s = s ^ 4;
+            for (;;) {
+                for (;;) { ++s; i4 = i3 + C_DY[s & 7] * W2 + C_DX[s & 7]; if (*i4 != 0) break; }
+                s &= 7;
+                if (s != prev_s || !approx_simple) { if (n < cap) { out_xy[2 * n] = x; out_xy[2 * n + 1] = y; } ++n; }
+                prev_s = s;
+                x += C_DX[s]; y += C_DY[s];
+                if (i4 == p0 && i3 == i1) break;
+                i3 = i4; s = (s + 4) & 7;
+            }
+        }
+    }
+    free(f); free(is_hole); free(parent);
+    return n;
+}

@@ -150,6 +150,43 @@ def main():
     rdets = post(_Rpn(), sc, deltas, anchors, ids, rcfg, (512, 512, 3))
     np.savez_compressed(os.path.join(HERE, "rpn_post.npz"), anchors=torch.cat(anchors).numpy(), deltas=torch.cat(deltas).numpy(),
                         scores=torch.cat(sc).numpy(), ids=torch.cat(ids).numpy(), dets=rdets.numpy())
+    # ---- mask2inst (tools/infer_wsi.py:51-54) with the real cv2 (the function body is the reference's own)
+    import cv2
+    m2i = extract("tools/infer_wsi.py", "mask2inst", extra={"cv2": cv2, "np": np})
+    rng = np.random.default_rng(5)
+
+    def blobs(h, w, n, r):
+        m = np.zeros((h, w), np.uint8)
+        yy, xx = np.mgrid[:h, :w]
+        for _ in range(n):
+            cy, cx = rng.uniform(0, h), rng.uniform(0, w)
+            a, b = rng.uniform(1, r, 2)
+            t = rng.uniform(0, np.pi)
+            u = (xx - cx) * np.cos(t) + (yy - cy) * np.sin(t)
+            v = -(xx - cx) * np.sin(t) + (yy - cy) * np.cos(t)
+            m |= ((u / a) ** 2 + (v / b) ** 2 <= 1).astype(np.uint8)
+        return m
+
+    cm = np.zeros((96, 96, 96), np.uint8)
+    for i in range(96):
+        kind = i % 4
+        if kind == 0:
+            cm[i, 20:60, 30:70] = rng.random((40, 40)) < rng.uniform(0.2, 0.8)          # noise: nested borders
+        elif kind == 1:
+            cm[i] = blobs(96, 96, int(rng.integers(1, 4)), 14)                           # nucleus-like
+        elif kind == 2:
+            cm[i] = (blobs(96, 96, 2, 30) & (1 - blobs(96, 96, 2, 10))) | blobs(96, 96, 1, 3)   # holes, islands, > 64 px
+        else:
+            cm[i] = cv2.dilate((rng.random((96, 96)) < 0.3).astype(np.uint8), np.ones((2, 2), np.uint8))
+        if not cm[i].any():
+            cm[i, 5, 7] = 1
+    cm[3] = 0; cm[3, 0, 0] = 1                      # single pixel at the corner
+    cm[7] = 1                                       # full frame
+    cm[11] = 0; cm[11, 40, 10:90] = 1               # 1-px line
+    cont = [m2i(m) for m in cm]
+    np.savez_compressed(os.path.join(HERE, "contours.npz"), masks=np.packbits(cm, axis=2),
+                        points=np.concatenate([c.reshape(-1, 2) for c in cont]).astype(np.int32),
+                        offsets=np.cumsum([0] + [c.shape[0] for c in cont]).astype(np.int64), cv2_version=cv2.__version__)
     print("golden vectors written to", HERE)
 
 

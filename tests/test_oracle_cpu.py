@@ -253,3 +253,30 @@ def test_rpn_post_process_golden(oracle):
     d = oracle.rpn_bbox_post_process(t("scores"), t("deltas"), t("anchors"), t("ids"), (512, 512, 3),
                                      dict(type="nms", iou_threshold=0.7), 300)
     assert torch.equal(d, t("dets"))
+
+
+def _golden_contours():
+    z = np.load(os.path.join(G, "contours.npz"))
+    cm = np.unpackbits(z["masks"], axis=2)[:, :, :96]
+    return cm, z["points"], z["offsets"]
+
+
+def test_contour_golden(oracle):
+    """mask2inst (tools/infer_wsi.py:51-54): golden made by running the reference function body on the real cv2."""
+    cm, pts, off = _golden_contours()
+    for i, m in enumerate(cm):
+        assert np.array_equal(oracle.mask2inst(m).reshape(-1, 2), pts[off[i]: off[i + 1]]), i
+
+
+def test_contour_live_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    for it in range(400):
+        h, w = rng.integers(1, 48, 2)
+        m = (rng.random((h, w)) < rng.uniform(0.1, 0.9)).astype(np.uint8)
+        if it % 3 == 0:
+            m = cv2.dilate(m, np.ones((2, 2), np.uint8))
+        for simple, flag in ((True, cv2.CHAIN_APPROX_SIMPLE), (False, cv2.CHAIN_APPROX_NONE)):
+            c, _ = cv2.findContours(m, cv2.RETR_TREE, flag)
+            ref = c[0].reshape(-1, 2) if len(c) else np.zeros((0, 2), np.int32)
+            assert np.array_equal(oracle.contour0(m, simple), ref)
