@@ -191,6 +191,7 @@ int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_
  * copy of every dense mask.  Suzuki-Abe border following on the bit rows; contour [0] of the tree
  * is the last outer border in raster order whose parent is the frame.
  *   bits [n,h,ceil(w/64)] uint64 (nuhtc_paste_masks BITS kind / nuhtc_pack_masks), device.
+ *   bbox [n,4] int32 or NULL: the tight boxes those calls return (saves a scan of every mask).
  *   out_xy [n,max_pts,2] int32 (x,y) in mask coordinates, out_count [n] int32: the contour's
  *   point count (0 for an empty mask).  A count above max_pts means the points were truncated.
  *   status [1] int32: 0 ok, 1 some contour longer than max_pts, 2 a mask wider/taller than 64 px
@@ -198,10 +199,43 @@ int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_
  * nuhtc_contour_rings: closed rings for nuhtc_merge: for every mask m with voff[m+1]-voff[m] = k > 0
  *   writes k vertices (contour points, then its first point again: infer_wsi.py:53) + origin[m]
  *   (tile coordinate, infer_wsi.py:531; NULL = 0) as fp64 at out[voff[m]..); k = 0 skips the mask. */
-int nuhtc_mask_contours(const uint64_t *bits, int64_t n, int h, int w, int max_pts, int32_t *out_xy,
+int nuhtc_mask_contours(const uint64_t *bits, const int32_t *bbox, int64_t n, int h, int w, int max_pts, int32_t *out_xy,
                         int32_t *out_count, int32_t *status, void *stream);
 int nuhtc_contour_rings(const int32_t *xy, const int32_t *count, const int64_t *voff, const int32_t *origin,
                         int64_t n, int max_pts, double *out, void *stream);
+
+/* ---- detection glue of the HTC test path ------------------------------------------------------
+ * The element-wise steps between the heavy ops (dozens of small torch kernels per batch in the
+ * reference), one launch each; every step is a separately rounded fp32 operation like the torch
+ * chain it replaces.
+ * nuhtc_delta2bbox: class-agnostic `delta2bbox` (mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:
+ *   163-260) as used by `regress_by_class` / `get_bboxes` (mmdet bbox_head.py:459-496, 330-380).
+ *   rois [K,5] (with_batch=1; column 0 is copied to out) or [K,4]; deltas [K,4]; means/stds 4 HOST
+ *   floats; max_h/max_w > 0 clamp to the frame (max_shape); divide_by != 0,1 divides the result
+ *   (rescale=True, bbox_head.py:373-376).  out has the shape of rois.
+ * nuhtc_multiclass_candidates: the candidate expansion of `multiclass_nms`
+ *   (nuhtc/models/bbox_head.py:12-60): boxes [K,4] (row stride box_stride floats), scores [K,score_stride] (first num_classes
+ *   columns), roi_tile = address of the batch-index column (stride tile_stride floats) ->
+ *   cand_* [K*num_classes] (box, score, label, tile) and groups = tile if score > score_thr else -1.
+ * nuhtc_detection_slots: `dets[:max_num]` (bbox_nms.py:98-100) without a host round trip: tile b's
+ *   r-th kept candidate (nuhtc_nms keep/group_start/group_count) lands in slot b*max_per_img + r;
+ *   empty slots get a box far outside the frame, score 0, tile -1, valid 0.  mask_rois [n,5] =
+ *   (max(tile,0), box * scale_factor) (htc_roi_head.py:296-300).
+ * nuhtc_tile_filter: margin / min_area filter of tools/infer_wsi.py:510-521 -> tile id or -1. */
+int nuhtc_delta2bbox(const float *rois, int with_batch, const float *deltas, int64_t K, const float *means,
+                     const float *stds, int max_h, int max_w, double wh_ratio_clip, float divide_by, float *out,
+                     void *stream);
+int nuhtc_multiclass_candidates(const float *boxes, int box_stride, const float *scores, int score_stride, const float *roi_tile,
+                                int tile_stride, int64_t K, int num_classes, float score_thr, float *cand_boxes,
+                                float *cand_scores, int64_t *cand_labels, int32_t *cand_tile, int32_t *groups,
+                                void *stream);
+int nuhtc_detection_slots(const int64_t *keep, const int64_t *group_start, const int64_t *group_count, int num_tiles,
+                          int max_per_img, const float *cand_boxes, const float *cand_scores, const int64_t *cand_labels,
+                          const int32_t *cand_tile, float scale_factor, float *det_boxes, float *det_scores,
+                          int64_t *det_labels, int32_t *det_tile, uint8_t *det_valid, int64_t *det_cand, float *mask_rois,
+                          void *stream);
+int nuhtc_tile_filter(const float *det_boxes, const int32_t *area, const int32_t *det_tile, int64_t D, int margin,
+                      int img_h, int img_w, int min_area, int32_t *tile_ids, void *stream);
 
 #ifdef __cplusplus
 }

@@ -43,8 +43,12 @@ SIGNATURES = {
     "nuhtc_merge": (_i, [_vp, _vp, _vp, _i64, _i64, _d, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_merge_graph": (_i, [_vp, _vp, _vp, _i64, _i64, _d, _i64, _vp, _vp, _vp, _c.POINTER(_i64), _vp, _vp, _sz, _vp]),
     "nuhtc_merge_rounds": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
-    "nuhtc_mask_contours": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "nuhtc_mask_contours": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "nuhtc_contour_rings": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "nuhtc_delta2bbox": (_i, [_vp, _i, _vp, _i64, _c.POINTER(_f * 4), _c.POINTER(_f * 4), _i, _i, _d, _f, _vp, _vp]),
+    "nuhtc_multiclass_candidates": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nuhtc_detection_slots": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nuhtc_tile_filter": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None
@@ -93,7 +97,7 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
 # ---- launch accounting: how many of OUR kernels each C-ABI call enqueues (bench.py reports the sum as
 # "gpu_launches"; library kernels such as cub's radix sort are not counted)
 LAUNCHES = {"n": 0}
-KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "attention_pool": 4, "roi_align": 1, "nms": 7, "paste": 2, "pack": 3, "mask_nms": 6, "merge": 16, "contours": 2, "rings": 1}
+KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "attention_pool": 4, "roi_align": 1, "nms": 7, "paste": 2, "pack": 3, "mask_nms": 6, "merge": 16, "contours": 2, "rings": 1, "glue": 1}
 
 
 def count(op: str, n: int = 1) -> None:

@@ -25,9 +25,10 @@ def _stream(t: torch.Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def mask_contours(bits: torch.Tensor, w: int, max_pts: int = 256, check: bool = True):
+def mask_contours(bits: torch.Tensor, w: int, max_pts: int = 256, check: bool = True, bbox: Optional[torch.Tensor] = None):
     """bits [n,h,ceil(w/64)] int64 bit rows (RoIStageResult.mask_bits / mask_nms.pack_masks) -> (xy [n,max_pts,2] int32,
-    count [n] int32, status [1] int32), all on the device.  ``check`` reads the status word (one small D2H)."""
+    count [n] int32, status [1] int32), all on the device.  ``bbox`` [n,4] int32: the tight boxes paste / pack return
+    (optional, saves a scan).  ``check`` reads the status word (one small D2H)."""
     if not bits.is_cuda:
         raise NuhtcError("mask_contours: CUDA tensors only (no CPU fallback)")
     assert bits.dtype == torch.int64 and bits.dim() == 3 and bits.is_contiguous()
@@ -36,8 +37,10 @@ def mask_contours(bits: torch.Tensor, w: int, max_pts: int = 256, check: bool = 
     xy = torch.empty((n, max_pts, 2), dtype=torch.int32, device=bits.device)
     cnt = torch.empty((n,), dtype=torch.int32, device=bits.device)
     status = torch.empty((1,), dtype=torch.int32, device=bits.device)
+    if bbox is not None:
+        assert bbox.dtype == torch.int32 and bbox.shape == (n, 4) and bbox.is_contiguous() and bbox.device == bits.device
     with torch.cuda.device(bits.device):
-        rc = lib().nuhtc_mask_contours(bits.data_ptr(), n, h, w, max_pts, xy.data_ptr(), cnt.data_ptr(), status.data_ptr(),
+        rc = lib().nuhtc_mask_contours(bits.data_ptr(), 0 if bbox is None else bbox.data_ptr(), n, h, w, max_pts, xy.data_ptr(), cnt.data_ptr(), status.data_ptr(),
                                        _stream(bits))
     _lib.check(rc, "nuhtc_mask_contours")
     count("contours")
@@ -54,8 +57,8 @@ def mask2inst(inst_map) -> np.ndarray:
     """tools/infer_wsi.py:51-54 for one dense mask: [n+1,1,2] int32 contour, first point repeated at the end."""
     from .mask_nms import pack_masks
     m = torch.as_tensor(np.ascontiguousarray(inst_map)).to(torch.uint8).cuda()[None]
-    bits, _, _ = pack_masks(m)
-    xy, cnt, _ = mask_contours(bits, m.shape[2], max_pts=max(8, 2 * int(m.shape[1] + m.shape[2]) + int(m.sum().item())))
+    bits, _, bbox = pack_masks(m)
+    xy, cnt, _ = mask_contours(bits, m.shape[2], bbox=bbox, max_pts=max(8, 2 * int(m.shape[1] + m.shape[2]) + int(m.sum().item())))
     c = xy[0, : int(cnt[0])].cpu().numpy().reshape(-1, 1, 2)
     return np.concatenate([c, c[[0]]], axis=0)
 

@@ -131,21 +131,21 @@ __device__ __forceinline__ bool mask_suppresses(const uint64_t *__restrict__ bit
     return __ddiv_rn((double)inter, (double)uni) > thr;
 }
 
-constexpr int kMWarps = 4;
+constexpr int kMWarps = 8; // warps per CTA; a CTA owns one 64 x 64 block of the pair matrix, warp w its rows w, w+8, ...
 
+// The pair test is a data-dependent loop over bit rows (most pairs are rejected on their boxes, overlapping ones read up to
+// 2 x h words), so the kernel is latency bound: one 64 x 64 block per CTA with its rows spread over 8 warps keeps ~30 warps
+// per SM busy for 16 tiles x 500 masks (4 warps walking 64 rows each left most SMs with 1-3 warps: 156 us -> see DESIGN).
 __global__ void __launch_bounds__(kMWarps * 32) mnms_mask_kernel(const uint64_t *__restrict__ bits, int h, int wpm,
                                                                  const int32_t *__restrict__ svals, const int32_t *__restrict__ sarea,
                                                                  const int4 *__restrict__ sbbox, const int *__restrict__ seg_start,
                                                                  int wpr, double thr, uint64_t *__restrict__ mask) {
     const int g = blockIdx.z;
     const int s0 = seg_start[g], n = min(seg_start[g + 1] - s0, wpr * 64);
-    const int rb = blockIdx.y;
-    const int cb = blockIdx.x * kMWarps + (threadIdx.x >> 5);
-    if (rb * 64 >= n) return;
-    if ((int)(blockIdx.x * kMWarps + kMWarps - 1) < rb) return;
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    if (rb * 64 >= n || cb < rb) return;
     __shared__ int4 r_bb[64];
     __shared__ int r_area[64], r_idx[64];
-    __shared__ uint64_t words[64][kMWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nrow = min(64, n - rb * 64);
     if (tid < 64) {
@@ -155,32 +155,21 @@ __global__ void __launch_bounds__(kMWarps * 32) mnms_mask_kernel(const uint64_t 
         r_idx[tid] = svals[p];
     }
     __syncthreads();
-    uint64_t w0 = 0, w1 = 0;
-    if (cb >= rb && cb * 64 < n) {
-        const int c0 = cb * 64 + lane, c1 = c0 + 32;
-        const bool v0 = c0 < n, v1 = c1 < n;
-        const int4 b0 = sbbox[s0 + (v0 ? c0 : 0)], b1 = sbbox[s0 + (v1 ? c1 : 0)];
-        const int a0 = sarea[s0 + (v0 ? c0 : 0)], a1 = sarea[s0 + (v1 ? c1 : 0)];
-        const int o0 = svals[s0 + (v0 ? c0 : 0)], o1 = svals[s0 + (v1 ? c1 : 0)];
-        for (int r = 0; r < nrow; ++r) {
-            const int row = rb * 64 + r;
-            const bool p0 = v0 && c0 > row && mask_suppresses(bits, h, wpm, r_idx[r], r_bb[r], r_area[r], o0, b0, a0, thr);
-            const bool p1 = v1 && c1 > row && mask_suppresses(bits, h, wpm, r_idx[r], r_bb[r], r_area[r], o1, b1, a1, thr);
-            const uint32_t lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
-            const uint64_t word = ((uint64_t)hi << 32) | lo;
-            if ((r & 31) == lane) {
-                if (r < 32) w0 = word; else w1 = word;
-            }
-        }
+    if (cb * 64 >= n) { // no columns: the rows' words of this block are zero
+        for (int r = tid; r < nrow; r += kMWarps * 32) mask[(size_t)(s0 + rb * 64 + r) * wpr + cb] = 0ull;
+        return;
     }
-    words[lane][warp] = w0;
-    words[lane + 32][warp] = w1;
-    __syncthreads();
-    if (tid < 64 && tid < nrow) {
-        uint64_t *dst = mask + (size_t)(s0 + rb * 64 + tid) * wpr + (size_t)blockIdx.x * kMWarps;
-#pragma unroll
-        for (int k = 0; k < kMWarps; ++k)
-            if ((int)(blockIdx.x * kMWarps + k) < wpr) dst[k] = words[tid][k];
+    const int c0 = cb * 64 + lane, c1 = c0 + 32;
+    const bool v0 = c0 < n, v1 = c1 < n;
+    const int4 b0 = sbbox[s0 + (v0 ? c0 : 0)], b1 = sbbox[s0 + (v1 ? c1 : 0)];
+    const int a0 = sarea[s0 + (v0 ? c0 : 0)], a1 = sarea[s0 + (v1 ? c1 : 0)];
+    const int o0 = svals[s0 + (v0 ? c0 : 0)], o1 = svals[s0 + (v1 ? c1 : 0)];
+    for (int r = warp; r < nrow; r += kMWarps) {
+        const int row = rb * 64 + r;
+        const bool p0 = v0 && c0 > row && mask_suppresses(bits, h, wpm, r_idx[r], r_bb[r], r_area[r], o0, b0, a0, thr);
+        const bool p1 = v1 && c1 > row && mask_suppresses(bits, h, wpm, r_idx[r], r_bb[r], r_area[r], o1, b1, a1, thr);
+        const uint32_t lo = __ballot_sync(0xffffffffu, p0), hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == 0) mask[(size_t)(s0 + row) * wpr + cb] = ((uint64_t)hi << 32) | lo;
     }
 }
 

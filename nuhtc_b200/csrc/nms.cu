@@ -40,34 +40,55 @@ __global__ void nms_init_kernel(int *cnt, int *gmax, int nseg, int ngroup, int32
     if (i == 0) *status = 0;
 }
 
-// class-segmented variant: the sort segment is (group, label); only the per-group max coordinate stays per group
+// class-segmented variant: the sort segment is (group, label); only the per-group max coordinate stays per group.
+// With `use_smem` the segment counts and group maxima are accumulated per CTA in shared memory first (80 000 candidates hit
+// only ~80 counters: per-element global atomics serialise on them), then flushed with one atomic per touched counter.
 __global__ void __launch_bounds__(256) nms_prep_seg_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores,
                                                            const int64_t *__restrict__ labels, const int32_t *__restrict__ groups,
-                                                           int64_t N, int G, int Cn, int need_max, int need_nonneg,
+                                                           int64_t N, int G, int Cn, int need_max, int need_nonneg, int use_smem,
                                                            uint64_t *__restrict__ keys, int32_t *__restrict__ vals, int *cnt,
                                                            int *gmax, int32_t *status) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int g = groups ? groups[i] : 0;
-    const long long lab = labels[i];
-    int seg;
-    if (g < 0) {
-        seg = G * Cn; // not a candidate
-    } else if (g >= G || lab < 0 || lab >= Cn) {
-        atomicExch(status, 2);
-        seg = G * Cn;
-        g = -1;
-    } else {
-        seg = g * Cn + (int)lab;
+    extern __shared__ int sh_prep[]; // [G*Cn + 1] counts, [G] maxima
+    const int S1 = G * Cn + 1;
+    const int neg_inf = float_ordered_int(-INFINITY);
+    if (use_smem) {
+        for (int t = threadIdx.x; t < S1 + G; t += blockDim.x) sh_prep[t] = t < S1 ? 0 : neg_inf;
+        __syncthreads();
     }
-    keys[i] = ((uint64_t)(uint32_t)seg << 32) | float_desc_key(scores[i]);
-    vals[i] = (int32_t)i;
-    atomicAdd(cnt + seg, 1);
-    if (g >= 0 && (need_max || need_nonneg)) {
-        const float4 b = boxes[i];
-        if (need_max) atomicMax(gmax + g, float_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
-        // class segments are only equivalent to the all-pairs test on offset boxes when no coordinate is negative
-        if (need_nonneg && fminf(fminf(b.x, b.y), fminf(b.z, b.w)) < 0.f) atomicExch(status, 3);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < N) {
+        int g = groups ? groups[i] : 0;
+        const long long lab = labels[i];
+        int seg;
+        if (g < 0) {
+            seg = G * Cn; // not a candidate
+        } else if (g >= G || lab < 0 || lab >= Cn) {
+            atomicExch(status, 2);
+            seg = G * Cn;
+            g = -1;
+        } else {
+            seg = g * Cn + (int)lab;
+        }
+        keys[i] = ((uint64_t)(uint32_t)seg << 32) | float_desc_key(scores[i]);
+        vals[i] = (int32_t)i;
+        atomicAdd((use_smem ? sh_prep : cnt) + seg, 1);
+        if (g >= 0 && (need_max || need_nonneg)) {
+            const float4 b = boxes[i];
+            if (need_max) atomicMax((use_smem ? sh_prep + S1 : gmax) + g, float_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+            // class segments are only equivalent to the all-pairs test on offset boxes when no coordinate is negative
+            if (need_nonneg && fminf(fminf(b.x, b.y), fminf(b.z, b.w)) < 0.f) atomicExch(status, 3);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < S1 + G; t += blockDim.x) {
+            const int v = sh_prep[t];
+            if (t < S1) {
+                if (v) atomicAdd(cnt + t, v);
+            } else if (v != neg_inf) {
+                atomicMax(gmax + (t - S1), v);
+            }
+        }
     }
 }
 
@@ -346,10 +367,13 @@ NUHTC_API int nuhtc_nms(const float *boxes, const float *scores, const int64_t *
     const int S = Cn > 0 ? G * Cn : G;
     const bool offs = mode == NUHTC_NMS_OFFSET || mode == NUHTC_NMS_PERCLASS;
     nms_init_kernel<<<(S + 256) / 256, 256, 0, st>>>(L.cnt, L.gmax, S + 1, G + 1, status);
-    if (Cn > 0)
-        nms_prep_seg_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, labels, groups, N, G, Cn, offs, mode == NUHTC_NMS_OFFSET,
-                                                L.keys_in, L.vals_in, L.cnt, L.gmax, status);
-    else
+    if (Cn > 0) {
+        const size_t prep_smem = sizeof(int) * (size_t)(S + 1 + G);
+        const int use_smem = prep_smem <= 32 * 1024;
+        nms_prep_seg_kernel<<<nb, 256, use_smem ? prep_smem : 0, st>>>((const float4 *)boxes, scores, labels, groups, N, G, Cn, offs,
+                                                                       mode == NUHTC_NMS_OFFSET, use_smem, L.keys_in, L.vals_in, L.cnt,
+                                                                       L.gmax, status);
+    } else
         nms_prep_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, groups, N, G, offs, L.keys_in, L.vals_in, L.cnt, L.gmax, status);
     segments_kernel<int64_t><<<1, 256, 0, st>>>(L.cnt, S, max_group_size, L.seg_start, Cn > 0 ? L.seg_count : group_start, status);
     int gbits = 0;

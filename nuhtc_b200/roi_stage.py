@@ -18,6 +18,8 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
+from . import det_ops
+from .contours import mask_contours
 from .mask_nms import mask_nms_device
 from .mask_paste import paste_masks
 from .mmcv_ops import nms_groups, roi_align_levels
@@ -45,6 +47,7 @@ class RoIStageConfig:
     img_shape: Tuple[int, int] = (512, 512)   # network frame (tile x scale_factor)
     ori_shape: Tuple[int, int] = (256, 256)   # tile frame
     scale_factor: float = 2.0
+    contour_max_pts: int = 0           # > 0: trace mask2inst contours of every detection slot (tools/infer_wsi.py:528)
     margin: int = 0                    # tools/infer_wsi.py --margin
     min_area: int = 10                 # tools/infer_wsi.py --min_area
     mask_nms_thr: float = 0.05         # tools/infer_wsi.py:526
@@ -65,15 +68,18 @@ class RoIStageResult:
     tile_count: torch.Tensor     # [B] int32
     det_valid: Optional[torch.Tensor] = None   # [D] bool: D = B*max_per_img slots, tile-major; invalid slots are padding
     det_cand: Optional[torch.Tensor] = None    # [D] int64 candidate id (roi*num_classes + label) of each slot
-    status: Optional[tuple] = None             # device status words of the NMS / mask-NMS launches
+    status: Optional[tuple] = None             # device status words of the NMS / mask-NMS (/ contour) launches
+    contour_xy: Optional[torch.Tensor] = None  # [D,contour_max_pts,2] int32 tile-frame contour points (cfg.contour_max_pts > 0)
+    contour_count: Optional[torch.Tensor] = None   # [D] int32
 
     def check(self) -> None:
         """Host-side check of the device status words (one small D2H)."""
         if self.status is not None:
-            for name, st in zip(("nms", "mask_nms"), self.status):
+            for name, st in zip(("nms", "mask_nms", "contours"), self.status):
                 v = int(st.item())
                 if v != 0:
-                    raise RuntimeError(f"{name} status {v}: a tile exceeded its declared capacity")
+                    raise RuntimeError(f"{name} status {v}: a tile exceeded its declared capacity" if name != "contours" else
+                                       f"contours status {v}: a contour exceeded contour_max_pts (1) or a mask its window (2)")
 
     def kept_indices(self) -> List[torch.Tensor]:
         ts, tc = self.tile_start.cpu().tolist(), self.tile_count.cpu().tolist()
@@ -91,7 +97,9 @@ class RoIStageResult:
         keep[:nk] = new_index[self.keep[:nk].long()].to(self.keep.dtype)
         return RoIStageResult(self.det_boxes[v], self.det_scores[v], self.det_labels[v], self.det_tile[v],
                               None if self.masks is None else self.masks[v], self.mask_bits[v], self.mask_area[v], keep,
-                              self.tile_start, self.tile_count, det_valid=None, det_cand=self.det_cand[v], status=None)
+                              self.tile_start, self.tile_count, det_valid=None, det_cand=self.det_cand[v], status=None,
+                              contour_xy=None if self.contour_xy is None else self.contour_xy[v],
+                              contour_count=None if self.contour_count is None else self.contour_count[v])
 
 
 def bbox2roi(bbox_list: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -196,21 +204,17 @@ class RoIStage:
             ms_scores.append(cls_score)
             if i < cfg.num_stages - 1:
                 # regress_by_class with reg_class_agnostic=True (mmdet bbox_head.py:459-496)
-                new = delta2bbox(rois[:, 1:], bbox_pred, K0["stds"][i], cfg.img_shape, means=K0["means"])
-                rois = torch.cat([rois[:, :1], new], dim=1)
+                rois = det_ops.delta2bbox(rois, bbox_pred, stds=cfg.stage_stds[i], max_shape=cfg.img_shape)
         cls_score = sum(ms_scores) / float(len(ms_scores))
         scores = self.score_fn(cls_score)
-        bboxes = delta2bbox(rois[:, 1:], bbox_pred, K0["stds"][cfg.num_stages - 1], cfg.img_shape, means=K0["means"])
-        bboxes = bboxes / cfg.scale_factor  # rescale=True: detections live in the tile frame
+        # rescale=True: detections live in the tile frame (bbox_head.py:373-376)
+        bboxes = det_ops.delta2bbox(rois, bbox_pred, stds=cfg.stage_stds[cfg.num_stages - 1], max_shape=cfg.img_shape,
+                                    divide_by=cfg.scale_factor)[:, 1:]
 
         # multiclass_nms for every tile at once (nuhtc/models/bbox_head.py:12-102): class-agnostic boxes are
         # expanded per class, candidates at or below score_thr are parked in a negative group, the rest go
         # through one grouped NMS launch with the per-image class offsets.
-        cand_boxes = bboxes[:, None, :].expand(K, C, 4).reshape(-1, 4)
-        cand_scores = scores[:, :C].reshape(-1)
-        cand_labels = K0["labels"].repeat(K)
-        cand_tile = tile_of_roi.repeat_interleave(C)
-        groups = torch.where(cand_scores > cfg.score_thr, cand_tile, torch.full_like(cand_tile, -1))
+        cand_boxes, cand_scores, cand_labels, cand_tile, groups = det_ops.multiclass_candidates(bboxes, scores, rois, C, cfg.score_thr)
         if max_rois_per_tile is None:
             max_rois_per_tile = int(torch.bincount(tile_of_roi.long(), minlength=B).max().item())
         with self._t("nms"):
@@ -221,28 +225,22 @@ class RoIStage:
         # max_per_img truncation WITHOUT a host round trip: every tile gets max_per_img detection slots; slot r of tile
         # b is its r-th kept candidate (score order) or invalid.  Invalid slots carry a box far outside the frame (RoIAlign
         # and paste see nothing there) and tile -1 (the mask NMS ignores them), so no kernel needs the counts on the host.
-        N = keep.numel()
         if cfg.max_per_img > 0:
-            M = cfg.max_per_img
-            r = torch.arange(M, device=dev)
-            cnt = torch.clamp(gcount, max=M)
-            det_valid = (r[None, :] < cnt[:, None]).reshape(-1)
-            idx = (gstart[:, None] + r[None, :]).clamp(max=N - 1).reshape(-1)
-            det_cand = torch.where(det_valid, keep[idx], torch.zeros_like(idx))
+            det_boxes, det_scores, det_labels, det_tile, det_valid, det_cand, mask_rois = det_ops.detection_slots(
+                keep, gstart, gcount, cfg.max_per_img, cand_boxes, cand_scores, cand_labels, cand_tile, cfg.scale_factor)
         else:  # unbounded detections per tile: sizes are data dependent, read them back
             host = torch.stack([gstart, gcount]).cpu()
             idx = torch.cat([torch.arange(s_, s_ + c_, device=dev) for s_, c_ in zip(host[0].tolist(), host[1].tolist())]) \
                 if int(host[1].sum()) > 0 else torch.zeros(0, dtype=torch.int64, device=dev)
             det_cand = keep[idx]
             det_valid = torch.ones_like(det_cand, dtype=torch.bool)
-        det_boxes = torch.where(det_valid[:, None], cand_boxes[det_cand], K0["far"]).contiguous()
-        det_scores = torch.where(det_valid, cand_scores[det_cand], K0["zero"]).contiguous()
-        det_labels = cand_labels[det_cand]
-        det_tile = torch.where(det_valid, cand_tile[det_cand], K0["minus1"]).contiguous()
+        if cfg.max_per_img <= 0:
+            det_boxes, det_scores, det_labels = cand_boxes[det_cand].contiguous(), cand_scores[det_cand].contiguous(), cand_labels[det_cand]
+            det_tile = cand_tile[det_cand].contiguous()
+            mask_rois = torch.cat([det_tile.to(torch.float32)[:, None], det_boxes * cfg.scale_factor], dim=1)
         D = det_boxes.shape[0]
 
         # mask branch: RoIAlign 14x14 on the detections (network frame), mask head, paste into the tile frame
-        mask_rois = torch.cat([det_tile.clamp(min=0).to(torch.float32)[:, None], det_boxes * cfg.scale_factor], dim=1)
         with self._t("roi_align_mask"):
             mask_feats = self.extract(feats, mask_rois, cfg.mask_out, cfg.mask_sampling_ratio)
         self._rec(mask_rois=mask_rois, mask_feats=mask_feats)
@@ -261,13 +259,17 @@ class RoIStage:
         self._rec(paste_probs=probs, paste_boxes=det_boxes)
 
         # tools/infer_wsi.py:510-521 margin / min_area filter, then per-tile mask NMS (:526)
-        ok = ((det_boxes[:, 0] >= cfg.margin) & (det_boxes[:, 1] >= cfg.margin) & (det_boxes[:, 2] <= W - cfg.margin) &
-              (det_boxes[:, 3] <= H - cfg.margin) & (area >= cfg.min_area))
-        tile_ids = torch.where(ok, det_tile, torch.full_like(det_tile, -1))
+        tile_ids = det_ops.tile_filter(det_boxes, area, det_tile, cfg.margin, H, W, cfg.min_area)
         cap = cfg.max_per_img if cfg.max_per_img > 0 else max(D, 1)
         with self._t("mask_nms"):
             keep2, tstart, tcount, st2 = mask_nms_device(bits, area, bbox, det_scores, W, cfg.mask_nms_thr, tile=tile_ids,
                                                          num_tiles=B, max_tile_size=cap)
         self._rec(mnms_tile=tile_ids)
+        cxy = ccnt = None
+        stat = (status, st2)
+        if cfg.contour_max_pts > 0:
+            with self._t("contours"):
+                cxy, ccnt, st3 = mask_contours(bits, W, cfg.contour_max_pts, check=False, bbox=bbox)
+            stat = (status, st2, st3)
         return RoIStageResult(det_boxes, det_scores, det_labels, det_tile, masks, bits, area, keep2, tstart, tcount,
-                              det_valid=det_valid, det_cand=det_cand, status=(status, st2))
+                              det_valid=det_valid, det_cand=det_cand, status=stat, contour_xy=cxy, contour_count=ccnt)

@@ -66,5 +66,9 @@ def roi_stage_cpu(feats: Sequence[torch.Tensor], rois: torch.Tensor, bbox_heads:
             keep = sel[torch.from_numpy(np.ascontiguousarray(k))]
         else:
             keep = sel
-        out.append(dict(det_boxes=det_boxes, det_scores=dets[:, 4], det_labels=labels, det_cand=det_cand, masks=masks, keep=keep))
+        # tools/infer_wsi.py:528-533: contour of every kept nucleus, contours shorter than 3 points dropped
+        mk = masks.numpy().astype(np.uint8)
+        contours = [O.mask2inst(mk[int(i)]) for i in keep]
+        out.append(dict(det_boxes=det_boxes, det_scores=dets[:, 4], det_labels=labels, det_cand=det_cand, masks=masks, keep=keep,
+                        contours=contours))
     return out

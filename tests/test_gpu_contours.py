@@ -13,8 +13,12 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 def _run(masks_u8, max_pts=512):
     from nuhtc_b200 import mask_contours, pack_masks
     m = torch.from_numpy(np.ascontiguousarray(masks_u8)).cuda()
-    bits, _, _ = pack_masks(m)
+    bits, _, bbox = pack_masks(m)
     xy, cnt, _ = mask_contours(bits, m.shape[2], max_pts=max_pts)
+    xy2, cnt2, _ = mask_contours(bits, m.shape[2], max_pts=max_pts, bbox=bbox)
+    assert torch.equal(cnt, cnt2)
+    live = torch.arange(xy.shape[1], device="cuda")[None, :] < cnt[:, None]          # entries beyond the count are not written
+    assert torch.equal(xy[live], xy2[live])
     xy, cnt = xy.cpu().numpy(), cnt.cpu().numpy()
     return [xy[i, :cnt[i]] for i in range(len(cnt))]
 
@@ -57,10 +61,13 @@ def test_nuclei_masks_from_paste(oracle):
     from nuhtc_b200 import synth, paste_masks
     from nuhtc_b200.contours import mask_contours
     boxes, probs, _ = synth.nuclei_masks(500, frame=256, seed=9)
-    bits = paste_masks(probs.cuda(), boxes.cuda(), 256, 256, thr=0.5, kind="bits")
+    bits, area, bbox = paste_masks(probs.cuda(), boxes.cuda(), 256, 256, thr=0.5, kind="bits", want_stats=True)
     dense = paste_masks(probs.cuda(), boxes.cuda(), 256, 256, thr=0.5, kind="bin").to(torch.uint8)
     xy, cnt, _ = mask_contours(bits, 256, max_pts=256)
-    xy, cnt, dense = xy.cpu().numpy(), cnt.cpu().numpy(), dense.cpu().numpy()
+    xy2, cnt2, _ = mask_contours(bits, 256, max_pts=256, bbox=bbox)          # tight boxes from the paste kernel
+    assert torch.equal(cnt, cnt2)
+    xy, cnt, dense, xy2 = xy.cpu().numpy(), cnt.cpu().numpy(), dense.cpu().numpy(), xy2.cpu().numpy()
+    assert all(np.array_equal(xy[i, :cnt[i]], xy2[i, :cnt[i]]) for i in range(len(cnt)))
     assert cnt.max() > 8
     for i in range(len(cnt)):
         assert np.array_equal(xy[i, :cnt[i]], oracle.contour0(dense[i]))

@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 def _setup(extractor, C, B=2, n_per=300, sr=0, max_per_img=100, score_thr=0.05):
     from nuhtc_b200 import synth
     from nuhtc_b200.roi_stage import RoIStageConfig
-    cfg = RoIStageConfig(extractor=extractor, bbox_sampling_ratio=sr, max_per_img=max_per_img, score_thr=score_thr)
+    cfg = RoIStageConfig(extractor=extractor, bbox_sampling_ratio=sr, max_per_img=max_per_img, score_thr=score_thr,
+                         contour_max_pts=256)
     feats = synth.fpn_levels(B, C, frame=512, seed=1)
     rois = synth.proposals(B, n_per, "nuclei" if extractor == "sum" else "routed", frame=512, seed=2)
     heads = synth.SyntheticHeads(B * n_per, seed=3)
@@ -74,6 +75,11 @@ def test_stage_op_boundaries(oracle, extractor, C, sr):
         ref = sel[oracle.mask_nms(m[sel], raw.det_scores.cpu().numpy()[sel], thr=0.05)] if len(sel) else sel
         assert (kept[b].cpu().numpy() == ref).all()
         assert len(ref) > 0
+    # mask2inst contours of every slot, on the GPU's own masks (tools/infer_wsi.py:528)
+    raw.check()
+    cxy, ccnt = raw.contour_xy.cpu().numpy(), raw.contour_count.cpu().numpy()
+    for i in range(0, m.shape[0], 3):
+        assert np.array_equal(cxy[i, :ccnt[i]], oracle.contour0(m[i]))
 
 
 def test_stage_end_to_end_vs_reference_flow(oracle):
