@@ -339,7 +339,10 @@ def run_ours(args):
     if ra_ms:
         ach = alg / (ra_ms * 1e-3) / 1e9
         roofline = {"kernel": "roi_align_pipe_kernel<7,64,1,5,32,1> (7x7 bbox RoIAlign, K=%d, C=%d)" % (K, C), "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the
+                    # `ncu --set full` capture summarised in profiles/r01_roialign_pipe.md (274.1 MB + 752.7 MB)
+                    "traffic": 1026811136 if (K == 16000 and C == 256 and args.dist == "nuclei") else None,
                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ra_ms, "launches_timed": len(ra), "peak_source": peak_src}
     paste = op_ms.get("paste", [])
     D = int(res.det_boxes.shape[0])

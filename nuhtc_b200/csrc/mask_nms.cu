@@ -123,8 +123,24 @@ __device__ __forceinline__ bool mask_suppresses(const uint64_t *__restrict__ bit
     if (x1 > x0 && y1 > y0) { // rleIou's bbIou prefilter: only boxes with positive overlap are walked
         const int w0 = x0 >> 6, w1 = (x1 - 1) >> 6;
         const uint64_t *pi = bits + ((size_t)oi * h + y0) * wpm, *pj = bits + ((size_t)oj * h + y0) * wpm;
-        for (int y = y0; y < y1; ++y, pi += wpm, pj += wpm)
-            for (int w = w0; w <= w1; ++w) inter += __popcll(__ldg(pi + w) & __ldg(pj + w));
+        // the rows are independent: 8 of them (16 loads) are kept in flight per lane, otherwise the walk is one L2 round
+        // trip per row (integer sums: the order does not matter)
+        for (int w = w0; w <= w1; ++w) {
+            const uint64_t *a = pi + w, *b = pj + w;
+            int y = y0, acc = 0;
+            for (; y < y1; y += 8, a += 8 * (size_t)wpm, b += 8 * (size_t)wpm) {
+                uint64_t va[8], vb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool live = y + u < y1;
+                    va[u] = live ? __ldg(a + (size_t)u * wpm) : 0ull;
+                    vb[u] = live ? __ldg(b + (size_t)u * wpm) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += __popcll(va[u] & vb[u]);
+            }
+            inter += acc;
+        }
     }
     if (inter == 0) return 0.0 > thr; // rleIou: i==0 -> u=1 -> 0/1
     const long long uni = (long long)ai + (long long)aj - inter;
@@ -274,7 +290,7 @@ NUHTC_API int nuhtc_mask_nms(const uint64_t *bits, const int32_t *area, const in
     NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, n, 0,
                                                32 + tbits, st));
     mnms_gather_kernel<<<nb, 256, 0, st>>>(area, bbox, L.vals_out, n, L.sarea, L.sbbox);
-    dim3 mgrid((wpr + kMWarps - 1) / kMWarps, wpr, T);
+    dim3 mgrid(wpr, wpr, T);
     mnms_mask_kernel<<<mgrid, kMWarps * 32, 0, st>>>(bits, h, wpm, L.vals_out, L.sarea, L.sbbox, L.seg_start, wpr, thr, L.mask);
     NUHTC_LAUNCH_CHECK();
     return launch_greedy_scan<int32_t>(L.mask, L.vals_out, L.seg_start, wpr, T, keep, tile_count, st);

@@ -1067,6 +1067,8 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
             }
             return launch_sep<7, 16, 1, 1, 8>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         }
+        // A/B on the box (K = 16000, nuclei): <14,8,2,2,2> 1.55 ms; one slice per thread at 4 CTAs/SM 1.94 ms, at 3 CTAs/SM
+        // 1.85 ms; a dense 196-float tile stride with float4 copy-out (no read conflicts) 2.35 ms
         if (v2) return launch_sep<14, 8, 2, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         return launch_sep<14, 16, 2, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
     }

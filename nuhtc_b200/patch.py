@@ -38,3 +38,18 @@ def patch_mmcv(verbose: bool = False):
     if verbose:
         print("nuhtc_b200.patch_mmcv:", ", ".join(done))
     return done
+
+
+def patch_wsi_tools(infer_wsi_module=None, nuclei_merge_module=None):
+    """Rebind the tile post-processing helpers of the reference's scripts: ``mask_nms`` and ``mask2inst`` of
+    tools/infer_wsi.py (:51-84) and ``merge_overlap`` of tools/nuclei_merge.py (:62-174).  Pass the imported modules."""
+    from . import mask2inst, mask_nms, merge_overlap
+    done = []
+    if infer_wsi_module is not None:
+        infer_wsi_module.mask_nms = mask_nms
+        infer_wsi_module.mask2inst = mask2inst
+        done += ["infer_wsi.mask_nms", "infer_wsi.mask2inst"]
+    if nuclei_merge_module is not None:
+        nuclei_merge_module.merge_overlap = merge_overlap
+        done.append("nuclei_merge.merge_overlap")
+    return done

@@ -151,6 +151,6 @@ def test_class_segmented_nms_equals_all_pairs(oracle):
         _, k_ref = oracle.batched_nms(B[idx], S[idx], Lb[idx], dict(type="nms", iou_threshold=0.5))
         assert torch.equal(b.cpu(), idx[k_ref]), g
     Bn = B.clone()
-    Bn[int((Gp >= 0).nonzero()[3])] -= 40.0
+    Bn[int((Gp >= 0).nonzero()[3])] -= 4000.0
     _, _, _, st = nb.nms_groups(Bn.cuda(), S.cuda(), Lb.cuda(), Gp.cuda(), G, 1200, 0.5, 0, "offset", num_classes=5)
     assert int(st.item()) == 3
