@@ -47,6 +47,7 @@ class RoIStageConfig:
     img_shape: Tuple[int, int] = (512, 512)   # network frame (tile x scale_factor)
     ori_shape: Tuple[int, int] = (256, 256)   # tile frame
     scale_factor: float = 2.0
+    overlap_dense_paste: bool = True   # write the dense masks on a forked stream beside the mask NMS / contour kernels
     contour_max_pts: int = 0           # > 0: trace mask2inst contours of every detection slot (tools/infer_wsi.py:528)
     margin: int = 0                    # tools/infer_wsi.py --margin
     min_area: int = 10                 # tools/infer_wsi.py --min_area
@@ -163,6 +164,12 @@ class RoIStage:
             self._consts[dev] = c
         return c
 
+    def _side_stream(self, dev):
+        st = self._consts.get(("side", dev))
+        if st is None:
+            st = self._consts[("side", dev)] = torch.cuda.Stream(device=dev)
+        return st
+
     def _t(self, name: str):
         return self.timer(name) if self.timer is not None else contextlib.nullcontext()
 
@@ -252,10 +259,20 @@ class RoIStage:
         # evaluating its ~1e3 reachable pixels twice.
         with self._t("paste_bits"):
             bits, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bits", want_stats=True)
+        # the dense frames are an output only (mask NMS and contours read the bit rows), and writing them is pure HBM
+        # traffic while the mask NMS scan and the contour walk are latency bound: they run side by side on a forked stream
         masks = None
+        side = None
         if cfg.dense_masks:
-            with self._t("paste"):
-                masks = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bin")
+            main = torch.cuda.current_stream(dev)
+            if cfg.overlap_dense_paste and not (self.timer is not None and getattr(self.timer, 'enabled', True)):  # per-op timing keeps one stream
+                side = self._side_stream(dev)
+                side.wait_stream(main)
+            with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                with self._t("paste"):
+                    masks = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bin")
+            if side is not None:
+                masks.record_stream(main)
         self._rec(paste_probs=probs, paste_boxes=det_boxes)
 
         # tools/infer_wsi.py:510-521 margin / min_area filter, then per-tile mask NMS (:526)
@@ -271,5 +288,7 @@ class RoIStage:
             with self._t("contours"):
                 cxy, ccnt, st3 = mask_contours(bits, W, cfg.contour_max_pts, check=False, bbox=bbox)
             stat = (status, st2, st3)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
         return RoIStageResult(det_boxes, det_scores, det_labels, det_tile, masks, bits, area, keep2, tstart, tcount,
                               det_valid=det_valid, det_cand=det_cand, status=stat, contour_xy=cxy, contour_count=ccnt)
