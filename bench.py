@@ -71,7 +71,10 @@ def workload_name(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons of this rank's GPU sampled DURING the timed region.  NVML in-process (initialised before
+    the timed region, one light query every 2 ms from a thread); a per-rank `nvidia-smi -lms` subprocess takes about a second
+    to start and holds driver locks while it does, which on an 8-GPU box stalled the launches of the very region it was
+    meant to observe.  Falls back to nvidia-smi when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -79,8 +82,40 @@ class ClockSampler:
         self.index = index
         self.lines = []
         self.proc = None
+        self.nvml = None
+        self.stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                flags = ",".join("Active" if rs & bit else "Not Active" for _, bit in names)
+                self.lines.append(f"{self.index},{sm},{self.max_sm},0,0,{flags}")
+            except Exception:
+                pass
+            self.stop.wait(0.002)
 
     def __enter__(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -95,6 +130,10 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *a):
+        if self.nvml is not None:
+            self.stop.set()
+            self.t.join(timeout=1)
+            return
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -290,12 +329,13 @@ def run_ours(args):
     lanes = [torch.cuda.Stream() for _ in range(max(1, args.inflight))] if (graph is not None and args.inflight > 1) else []
 
     # ---- timed region: exactly K steps + the one merge
+    sampler = ClockSampler(local)   # NVML is initialised here, outside the timed region
     _lib.LAUNCHES["n"] = 0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with sampler as clocks:
         e0.record()
         main = torch.cuda.current_stream()
         for ln in lanes:
@@ -310,12 +350,20 @@ def run_ours(args):
                 res = one_step()
         for ln in lanes:
             main.wait_stream(ln)
+        e_steps = torch.cuda.Event(enable_timing=True)
+        e_steps.record()
         kept = merge_step()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
     ms = e0.elapsed_time(e1)
+    steps_ms = e0.elapsed_time(e_steps)   # this rank's K steps without the merge (the merge waits for the slowest rank)
+    per_rank_steps = [steps_ms]
+    if world > 1:
+        tl = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([steps_ms], device=dev, dtype=torch.float64))
+        per_rank_steps = [float(t.item()) for t in tl]
     launches = _lib.LAUNCHES["n"] + (launches_per_step * args.steps if graph is not None else 0)
 
     # ---- per-kernel durations (CUDA events cannot bracket nodes inside a graph): the same K steps are repeated eagerly
@@ -409,6 +457,7 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (356 MB FPN levels + 0.8 GB RoIAlign output per launch)",
                            "parallelism": f"tile stripes over {world} GPU(s), seam nuclei all-gathered for the merge"},
                 "roofline": roofline, "roofline_other": extra, "breakdown_ms_per_step": breakdown,
+                "per_rank_steps_ms": [round(v, 3) for v in per_rank_steps],
                 "timing": {"timed_region": ("cuda graph replay of the captured step" + (f", {len(lanes)} batches in flight on {len(lanes)} streams"
                                                                                           if lanes else "")) if graph is not None else "eager",
                            "eager_instrumented_ms_per_step": eager_ms / args.steps,

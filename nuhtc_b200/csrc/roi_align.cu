@@ -567,8 +567,8 @@ struct RingPos {
     }
 };
 
-// consumer: staged rows for a thread with NX x-taps (NX == 0: runtime count, weights from the slot) and PB (<= 7)
-// output rows whose dense weights sit at wyd[row][0..7]
+// consumer: staged rows for a thread with NX x-taps (NX == 0: runtime count, weights from the slot) and PB (<= 14)
+// output rows whose dense weights sit at wyd[row][0..7] (rows 0..6) and wyd[row][8..15] (rows 7..13)
 template <int NX, int PB, int NS, int WYS>
 __device__ __forceinline__ void staged_rows(const float *ring, int stage_floats, int CC, int y0, int y1, int xoff, int q,
                                             const float *s_wxp, const float *s_wyd, float2 (&acc)[PB][1][2], uint32_t full0,
@@ -598,12 +598,18 @@ __device__ __forceinline__ void staged_rows(const float *ring, int stage_floats,
                     t1 = ffma2(w, make_float2(v.z, v.w), t1);
                 }
             }
-            const float4 wa = *reinterpret_cast<const float4 *>(s_wyd), wb = *reinterpret_cast<const float4 *>(s_wyd + 4);
-            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            constexpr int NG = (PB + 6) / 7; // groups of up to 7 output rows, 8 weight floats each
+            float w[NG * 8];
+#pragma unroll
+            for (int gI = 0; gI < NG; ++gI) {
+                const float4 wa = *reinterpret_cast<const float4 *>(s_wyd + 8 * gI), wb = *reinterpret_cast<const float4 *>(s_wyd + 8 * gI + 4);
+                w[8 * gI + 0] = wa.x; w[8 * gI + 1] = wa.y; w[8 * gI + 2] = wa.z; w[8 * gI + 3] = wa.w;
+                w[8 * gI + 4] = wb.x; w[8 * gI + 5] = wb.y; w[8 * gI + 6] = wb.z; w[8 * gI + 7] = wb.w;
+            }
 #pragma unroll
             for (int i = 0; i < PB; ++i) {
-                acc[i][0][0] = ffma2(w[i], t0, acc[i][0][0]);
-                acc[i][0][1] = ffma2(w[i], t1, acc[i][0][1]);
+                acc[i][0][0] = ffma2(w[i / 7 * 8 + i % 7], t0, acc[i][0][0]);
+                acc[i][0][1] = ffma2(w[i / 7 * 8 + i % 7], t1, acc[i][0][1]);
             }
         }
         __syncwarp();
@@ -620,8 +626,12 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                           const __grid_constant__ RoiTmaps tm) {
     constexpr int CC = NQ * 4;
     constexpr int PP = SepCfg<P>::PP;
-    const bool kBulkStore = (SepCfg<P>::S == PP) && bulk_store_flag != 0;            // contiguous tile == contiguous global chunk
-    constexpr int S = SepCfg<P>::S;
+    // tile stride: the padded one is conflict-free for the transposition; the dense one (== PP) leaves as ONE asynchronous
+    // bulk store.  P = 14 with 128-channel chunks takes the dense stride although its transposition then is 4-way
+    // conflicted (channel rows must stay 16-byte aligned for the bulk copy): the store overlaps the next chunk's rows.
+    constexpr bool kDenseTile = (P == 14 && NQ == 32);
+    constexpr int S = kDenseTile ? PP : SepCfg<P>::S;
+    const bool kBulkStore = (S == PP) && (bulk_store_flag & 1) != 0;            // contiguous tile == contiguous global chunk
     constexpr int NWORK = NQ * P * PHS;              // consumer threads that own outputs
     constexpr int NCONS = (NWORK + 31) / 32 * 32;    // padded to whole warps: the tail threads only keep the barriers company
     constexpr int CONS_WARPS = NCONS / 32;
@@ -655,7 +665,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                            // (nchunk > 1 is only launched with nlev == 1)
     unsigned itemctr = 0;
     constexpr int WYS = (P + 6) / 7 * 8;
-    static_assert(PB <= 7, "a consumer owns at most 7 output rows");
+    static_assert(PB <= 7 || (PB == P && P <= 14), "a consumer owns at most 7 output rows, or all of them");
 
     if (tid >= NCONS + 32) {
         // =========================== copy warp: streams the window rows of every staged item ===========================
@@ -782,7 +792,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
     for (int i = 0; i < PB; ++i) acc[i][0][0] = acc[i][0][1] = make_float2(0.f, 0.f);
     RingPos rp{0u, 0u};
     // flush constants of this thread: the lane-rotated channel order and the tile offsets that go with it
-    const int rot = (lane >> 3) - (lane / NQ);
+    const int rot = kDenseTile ? ((q >> 1) & 3) : (lane >> 3) - (lane / NQ);
     const bool rot1 = (rot & 1) != 0, rot2 = (rot & 2) != 0;
     int toff[4];
 #pragma unroll
@@ -817,6 +827,12 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
         } else {
             asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
             constexpr int N4 = CC * PP / 4;
+            if (bulk_store_flag & 2) { // A/B: conflict-free scalar reads of the padded tile, 32-bit coalesced stores
+                for (int e = tid; e < CC * PP; e += NCONS) {
+                    const int c = e / PP;
+                    __stcs(outp + e, s_tile[c * S + (e - c * PP)]);
+                }
+            } else
             for (int i = tid; i < N4; i += NCONS) {
                 int c = (4 * i) / PP, e = 4 * i - c * PP;
                 float t[4];
@@ -968,7 +984,8 @@ static int launch_pipe(const RoiLevels &lv, int B, int C, const float *rois, int
     if (C / (NQ * 4) > 1) {
         if (WMAX > tmap_box_px(kTmapBoxes - 1) || !build_tmaps(lv, B, C, NQ * 4, &tm)) return 1; // caller falls back
     }
-    const size_t smem = sizeof(float) * ((size_t)NS * WMAX * NQ * 4 + NQ * 4 * SepCfg<P>::S) + kPipeSlots * sizeof(PipeSlot<P>) +
+    const size_t smem = sizeof(float) * ((size_t)NS * WMAX * NQ * 4 + NQ * 4 * ((P == 14 && NQ == 32) ? P * P : SepCfg<P>::S)) +
+                        kPipeSlots * sizeof(PipeSlot<P>) +
                         sizeof(uint64_t) * (2 * NS + 2 * kPipeSlots) + 128;
     auto kern = roi_align_pipe_kernel<P, NQ, PHS, NS, WMAX, MINB>;
     constexpr int nthreads = (NQ * P * PHS + 31) / 32 * 32 + 64;
@@ -1046,9 +1063,16 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
         } else if (C == 64) {
             rc = launch_pipe<14, 16, 2, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         } else if ((mode == NUHTC_ROI_ROUTE || L == 1) && getenv("NUHTC_RA_TMAP")) {
-            // 64-channel chunks fetched through 2-D tensor maps (cp.async.bulk.tensor).  Correct, but measured slower than
-            // the non-pipelined kernel for 14x14 at C=256 (1.74 vs 1.52 ms at K=16000), so it is opt-in.
-            rc = launch_pipe<14, 16, 2, 12, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+            // Channel chunks fetched through 2-D tensor maps (cp.async.bulk.tensor), opt-in.  K=16000, C=256 on the box:
+            //   =1  64-channel chunks, two row halves per thread column      1.81 ms nuclei / 3.51 ms routed
+            //   =2  128-channel chunks, dense tile + one async bulk store    1.47 ms nuclei / 4.42 ms routed
+            //   non-pipelined roi_align_sep_kernel<14,8,2,2,2> (default)     1.55 ms nuclei / 2.16 ms routed
+            // =2 wins 5 % on nucleus-sized windows but its 24-px ring rows send the wide windows of large RoIs down the
+            // direct-load path, so the non-pipelined kernel stays the default for the mask branch.
+            if (getenv("NUHTC_RA_TMAP")[0] == '2')   // 128-channel halves, every thread owns all 14 rows of its column
+                rc = launch_pipe<14, 32, 1, 8, 24, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
+            else
+                rc = launch_pipe<14, 16, 2, 12, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest_scale, out, bias, st);
         }
         if (rc != 1) return rc;
     }

@@ -21,6 +21,9 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+import time
+
 import torch
 import torch.distributed as dist
 
@@ -96,6 +99,16 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     from .slide import stripe_rows
     engine = engine or CudaMergeEngine()
     dev = xy.device
+    trace = os.environ.get("NUHTC_SEAM_TRACE") == "1" and rank == 0   # host wall-clock per phase (synchronises: debugging only)
+    marks = []
+
+    def mark(name):
+        if trace:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     N = score.numel()
     gid = torch.as_tensor(shard["gid"], dtype=torch.int64, device=dev)
     cnt = voff[1:] - voff[:-1]
@@ -121,6 +134,7 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
         bxy = xy[src]
     else:
         bxy = xy[:0]
+    mark("band")
     # ---- one exchange of the band nuclei (counts, then padded records)
     sizes = torch.tensor([nb, nv], dtype=torch.int64, device=dev)
     all_sizes = [torch.empty_like(sizes) for _ in range(world)]
@@ -133,37 +147,33 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     g_meta = _all_gather_ragged(meta, ncounts, group)
     g_xy = _all_gather_ragged(bxy, vcounts, group)
 
-    # ---- halo = foreign band nuclei that reach into MY stripe
+    mark("exchange")
+    # ---- halo = foreign band nuclei that reach into MY stripe (one pass over the concatenated records of all ranks)
     me = extents[rank]
-    h_score, h_gid, h_cnt, h_xy, h_src = [], [], [], [], []
-    for q in range(world):
-        if q == rank or ncounts[q] == 0 or me is None:
-            continue
-        m = g_meta[q]
-        take = (m[:, 4] >= me[0]) & (m[:, 3] <= me[1])
-        tidx = take.nonzero().squeeze(1)
-        if tidx.numel() == 0:
-            continue
-        c = m[:, 2].to(torch.int64)
+    f_meta = torch.cat(g_meta) if sum(ncounts) else torch.zeros((0, 5), dtype=torch.float64, device=dev)
+    f_xy = torch.cat(g_xy) if sum(vcounts) else xy[:0]
+    f_rank = torch.repeat_interleave(torch.arange(world, device=dev), torch.as_tensor(ncounts, device=dev))
+    if me is not None and f_meta.shape[0]:
+        take = (f_meta[:, 4] >= me[0]) & (f_meta[:, 3] <= me[1]) & (f_rank != rank)
+        halo_flat = take.nonzero().squeeze(1)          # positions in the concatenated band list (rank-major, band order)
+    else:
+        halo_flat = torch.zeros(0, dtype=torch.int64, device=dev)
+    H = int(halo_flat.numel())
+    if H:
+        c = f_meta[:, 2].to(torch.int64)
         off = torch.zeros(c.numel() + 1, dtype=torch.int64, device=dev)
         off[1:] = torch.cumsum(c, 0)
-        tc = c[tidx]
-        tseg = torch.repeat_interleave(torch.arange(tidx.numel(), device=dev), tc)
-        toff = torch.zeros(tidx.numel() + 1, dtype=torch.int64, device=dev)
+        tc = c[halo_flat]
+        toff = torch.zeros(H + 1, dtype=torch.int64, device=dev)
         toff[1:] = torch.cumsum(tc, 0)
-        vsrc = off[:-1][tidx][tseg] + (torch.arange(int(toff[-1]), device=dev) - toff[:-1][tseg])
-        h_score.append(m[tidx, 0]); h_gid.append(m[tidx, 1].to(torch.int64)); h_cnt.append(tc); h_xy.append(g_xy[q][vsrc])
-        h_src.append(torch.stack([torch.full_like(tidx, q), tidx], dim=1))
-    H = int(sum(t.numel() for t in h_score))
-    if H:
-        a_score = torch.cat([score] + h_score)
-        a_gid = torch.cat([gid] + h_gid)
-        a_cnt = torch.cat([cnt] + h_cnt)
-        a_xy = torch.cat([xy] + h_xy)
-        halo_src = torch.cat(h_src)
+        tseg = torch.repeat_interleave(torch.arange(H, device=dev), tc)
+        vsrc = off[:-1][halo_flat][tseg] + (torch.arange(tseg.numel(), device=dev) - toff[:-1][tseg])
+        a_score = torch.cat([score, f_meta[halo_flat, 0]])
+        a_gid = torch.cat([gid, f_meta[halo_flat, 1].to(torch.int64)])
+        a_cnt = torch.cat([cnt, tc])
+        a_xy = torch.cat([xy, f_xy[vsrc]])
     else:
         a_score, a_gid, a_cnt, a_xy = score, gid, cnt, xy
-        halo_src = torch.zeros((0, 2), dtype=torch.int64, device=dev)
     M = N + H
     # order the local set by global id so that equal scores are ranked like the single-GPU merge (lower index first)
     perm = torch.argsort(a_gid, stable=True)
@@ -179,7 +189,9 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     inv = torch.empty_like(perm)
     inv[perm] = torch.arange(M, device=dev)          # position of local-set element i in the permuted arrays
 
+    mark("halo+permute")
     indeg, in_off, in_list = engine.graph(p_xy, p_voff, p_score, overlap_threshold)
+    mark("graph")
     frozen = torch.zeros(M, dtype=torch.uint8, device=dev)
     frozen[inv[N:]] = 1
     state = torch.where((indeg[:M] == 0) & (frozen == 0), 1, 0).to(torch.uint8)
@@ -191,16 +203,16 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     for _ in range(1 << 20):
         g_state = _all_gather_ragged(state[band_pos], ncounts, group)
         if H:
-            flat_off = [0]
-            for c in ncounts:
-                flat_off.append(flat_off[-1] + c)
-            flat = torch.cat(g_state)
-            state[halo_pos] = flat[torch.as_tensor(flat_off[:-1], device=dev)[halo_src[:, 0]] + halo_src[:, 1]]
+            state[halo_pos] = torch.cat(g_state)[halo_flat]
         remaining = engine.rounds(in_off, indeg, in_list, frozen, state, 4)
         tot = remaining.clone()
         dist.all_reduce(tot, group=group)
         if int(tot.item()) == 0:
             break
+    mark("resolve")
+    if trace:
+        print("seam trace (ms):", ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])),
+              f"| own {N} band {nb} halo {H}", flush=True)
     kept_local = (state[own_pos] == 1).nonzero().squeeze(1)
     order = torch.argsort(-score[kept_local], stable=True)
     kept_local = kept_local[order]
