@@ -98,11 +98,13 @@ int nuhtc_attention_pool(const float *feat_nhwc, int B, int H, int W, int C, con
  *                               (batched_nms at/above split_thr: one nms per class).
  *   Suppression test: inter/(area_i+area_j-inter) > iou_thr with IEEE fp32 division, areas
  *   (x2-x1+offset)*(y2-y1+offset); order = score descending, ties lower index first.
- *   max_group_size  upper bound on the number of boxes in any one group (N if unknown).
+ *   max_group_size  upper bound on the number of boxes in any one sort segment: a group, or with
+ *          num_classes > 0 one (group, class) list (the group bound always works; N if unknown).
+ *          It sizes the pair matrix, so a tight bound matters.
  *   keep   [N] int64 out: group g's kept ORIGINAL indices, score-descending, are
  *          keep[group_start[g] .. group_start[g]+group_count[g])
  *   group_start, group_count  [num_groups] int64 out (device)
- *   status [1] int32 out (device): 0 ok, 1 = a group exceeded max_group_size.
+ *   status [1] int32 out (device): 0 ok, 1 = a segment exceeded max_group_size.
  *   ws/ws_bytes from nuhtc_nms_workspace_bytes(N, num_groups, max_group_size). */
 #define NUHTC_NMS_AGNOSTIC 0
 #define NUHTC_NMS_OFFSET 1
@@ -192,6 +194,8 @@ int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_
  * is the last outer border in raster order whose parent is the frame.
  *   bits [n,h,ceil(w/64)] uint64 (nuhtc_paste_masks BITS kind / nuhtc_pack_masks), device.
  *   bbox [n,4] int32 or NULL: the tight boxes those calls return (saves a scan of every mask).
+ *   select [n] uint8 or NULL: masks with select[m] == 0 are skipped (count 0); infer_wsi.py traces
+ *   only the survivors of the mask NMS (nuhtc_keep_flags turns its keep lists into this array).
  *   out_xy [n,max_pts,2] int32 (x,y) in mask coordinates, out_count [n] int32: the contour's
  *   point count (0 for an empty mask).  A count above max_pts means the points were truncated.
  *   status [1] int32: 0 ok, 1 some contour longer than max_pts, 2 a mask wider/taller than 64 px
@@ -199,7 +203,7 @@ int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_
  * nuhtc_contour_rings: closed rings for nuhtc_merge: for every mask m with voff[m+1]-voff[m] = k > 0
  *   writes k vertices (contour points, then its first point again: infer_wsi.py:53) + origin[m]
  *   (tile coordinate, infer_wsi.py:531; NULL = 0) as fp64 at out[voff[m]..); k = 0 skips the mask. */
-int nuhtc_mask_contours(const uint64_t *bits, const int32_t *bbox, int64_t n, int h, int w, int max_pts, int32_t *out_xy,
+int nuhtc_mask_contours(const uint64_t *bits, const int32_t *bbox, const uint8_t *select, int64_t n, int h, int w, int max_pts, int32_t *out_xy,
                         int32_t *out_count, int32_t *status, void *stream);
 int nuhtc_contour_rings(const int32_t *xy, const int32_t *count, const int64_t *voff, const int32_t *origin,
                         int64_t n, int max_pts, double *out, void *stream);
@@ -221,7 +225,10 @@ int nuhtc_contour_rings(const int32_t *xy, const int32_t *count, const int64_t *
  *   r-th kept candidate (nuhtc_nms keep/group_start/group_count) lands in slot b*max_per_img + r;
  *   empty slots get a box far outside the frame, score 0, tile -1, valid 0.  mask_rois [n,5] =
  *   (max(tile,0), box * scale_factor) (htc_roi_head.py:296-300).
- * nuhtc_tile_filter: margin / min_area filter of tools/infer_wsi.py:510-521 -> tile id or -1. */
+ * nuhtc_tile_filter: margin / min_area filter of tools/infer_wsi.py:510-521 -> tile id or -1.
+ * nuhtc_keep_flags: flags [n] uint8 = 1 for the indices listed in nuhtc_mask_nms's keep lists
+ *   (keep[tile_start[t] .. +tile_count[t]) for every tile), 0 elsewhere: the `seg_mask[nms_idx]`
+ *   selection of infer_wsi.py:527-531 without a host round trip. */
 int nuhtc_delta2bbox(const float *rois, int with_batch, const float *deltas, int64_t K, const float *means,
                      const float *stds, int max_h, int max_w, double wh_ratio_clip, float divide_by, float *out,
                      void *stream);
@@ -236,6 +243,8 @@ int nuhtc_detection_slots(const int64_t *keep, const int64_t *group_start, const
                           void *stream);
 int nuhtc_tile_filter(const float *det_boxes, const int32_t *area, const int32_t *det_tile, int64_t D, int margin,
                       int img_h, int img_w, int min_area, int32_t *tile_ids, void *stream);
+int nuhtc_keep_flags(const int32_t *keep, const int32_t *tile_start, const int32_t *tile_count, int num_tiles,
+                     int max_tile_size, int64_t n, uint8_t *flags, void *stream);
 
 #ifdef __cplusplus
 }

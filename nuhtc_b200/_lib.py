@@ -43,12 +43,13 @@ SIGNATURES = {
     "nuhtc_merge": (_i, [_vp, _vp, _vp, _i64, _i64, _d, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_merge_graph": (_i, [_vp, _vp, _vp, _i64, _i64, _d, _i64, _vp, _vp, _vp, _c.POINTER(_i64), _vp, _vp, _sz, _vp]),
     "nuhtc_merge_rounds": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
-    "nuhtc_mask_contours": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "nuhtc_mask_contours": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "nuhtc_contour_rings": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "nuhtc_delta2bbox": (_i, [_vp, _i, _vp, _i64, _c.POINTER(_f * 4), _c.POINTER(_f * 4), _i, _i, _d, _f, _vp, _vp]),
     "nuhtc_multiclass_candidates": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nuhtc_detection_slots": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nuhtc_tile_filter": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "nuhtc_keep_flags": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp]),
 }
 
 _lib = None

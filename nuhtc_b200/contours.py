@@ -25,10 +25,12 @@ def _stream(t: torch.Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def mask_contours(bits: torch.Tensor, w: int, max_pts: int = 256, check: bool = True, bbox: Optional[torch.Tensor] = None):
+def mask_contours(bits: torch.Tensor, w: int, max_pts: int = 256, check: bool = True, bbox: Optional[torch.Tensor] = None,
+                  select: Optional[torch.Tensor] = None):
     """bits [n,h,ceil(w/64)] int64 bit rows (RoIStageResult.mask_bits / mask_nms.pack_masks) -> (xy [n,max_pts,2] int32,
     count [n] int32, status [1] int32), all on the device.  ``bbox`` [n,4] int32: the tight boxes paste / pack return
-    (optional, saves a scan).  ``check`` reads the status word (one small D2H)."""
+    (optional, saves a scan).  ``select`` [n] uint8/bool: only these masks are traced (the others get count 0).  ``check``
+    reads the status word (one small D2H)."""
     if not bits.is_cuda:
         raise NuhtcError("mask_contours: CUDA tensors only (no CPU fallback)")
     assert bits.dtype == torch.int64 and bits.dim() == 3 and bits.is_contiguous()
@@ -39,8 +41,13 @@ def mask_contours(bits: torch.Tensor, w: int, max_pts: int = 256, check: bool = 
     status = torch.empty((1,), dtype=torch.int32, device=bits.device)
     if bbox is not None:
         assert bbox.dtype == torch.int32 and bbox.shape == (n, 4) and bbox.is_contiguous() and bbox.device == bits.device
+    if select is not None:
+        if select.dtype == torch.bool:
+            select = select.view(torch.uint8)
+        assert select.dtype == torch.uint8 and select.shape == (n,) and select.is_contiguous() and select.device == bits.device
     with torch.cuda.device(bits.device):
-        rc = lib().nuhtc_mask_contours(bits.data_ptr(), 0 if bbox is None else bbox.data_ptr(), n, h, w, max_pts, xy.data_ptr(), cnt.data_ptr(), status.data_ptr(),
+        rc = lib().nuhtc_mask_contours(bits.data_ptr(), 0 if bbox is None else bbox.data_ptr(),
+                                       0 if select is None else select.data_ptr(), n, h, w, max_pts, xy.data_ptr(), cnt.data_ptr(), status.data_ptr(),
                                        _stream(bits))
     _lib.check(rc, "nuhtc_mask_contours")
     count("contours")

@@ -32,7 +32,8 @@ __device__ __forceinline__ uint64_t win_word(const uint64_t *__restrict__ mb, in
 
 // pass: 0 = small windows, larger ones are an error (no large pass possible); 1 = small windows, larger ones skipped;
 //       2 = only the larger ones
-__global__ void __launch_bounds__(32) contour_kernel(const uint64_t *__restrict__ bits, const int32_t *__restrict__ bbox, int64_t N,
+__global__ void __launch_bounds__(32) contour_kernel(const uint64_t *__restrict__ bits, const int32_t *__restrict__ bbox,
+                                                     const uint8_t *__restrict__ select, int64_t N,
                                                      int h, int wpm, int pass,
                                                      int max_pts, int32_t *__restrict__ out_xy, int32_t *__restrict__ out_count,
                                                      int32_t *__restrict__ status) {
@@ -41,6 +42,10 @@ __global__ void __launch_bounds__(32) contour_kernel(const uint64_t *__restrict_
     const int lane = threadIdx.x;
     for (int64_t m = blockIdx.x; m < N; m += gridDim.x) {
         const uint64_t *mb = bits + (size_t)m * h * wpm;
+        if (select && !select[m]) { // not asked for (e.g. suppressed by the mask NMS): no contour
+            if (pass != 2 && lane == 0) out_count[m] = 0;
+            continue;
+        }
         // ---- tight window of the mask
         int ymin = h, ymax = -1, xmin = wpm * 64, xmax = -1;
         if (bbox) { // tight box from the paste / pack kernels: x0, y0, x1, y1 (exclusive), all 0 for an empty mask
@@ -217,7 +222,7 @@ __global__ void contour_rings_kernel(const int32_t *__restrict__ xy, const int32
 
 } // namespace
 
-NUHTC_API int nuhtc_mask_contours(const uint64_t *bits, const int32_t *bbox, int64_t n, int h, int w, int max_pts, int32_t *out_xy,
+NUHTC_API int nuhtc_mask_contours(const uint64_t *bits, const int32_t *bbox, const uint8_t *select, int64_t n, int h, int w, int max_pts, int32_t *out_xy,
                                   int32_t *out_count, int32_t *status, void *stream) {
     NUHTC_CHECK_ARG(n >= 0 && h >= 1 && w >= 1 && max_pts >= 1 && status != nullptr, "mask_contours: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -237,12 +242,12 @@ NUHTC_API int nuhtc_mask_contours(const uint64_t *bits, const int32_t *bbox, int
     const bool large_ok = need_large && large_smem <= (size_t)max_optin;
     const unsigned grid = (unsigned)(n < (int64_t)nuhtc_sm_count() * 32 ? n : (int64_t)nuhtc_sm_count() * 32);
     NUHTC_CHECK_ARG(((uintptr_t)bbox & 15) == 0, "mask_contours: bbox must be 16-byte aligned");
-    contour_kernel<<<grid, 32, small_smem, st>>>(bits, bbox, n, h, wpm, need_large ? (large_ok ? 1 : 0) : 1, max_pts, out_xy, out_count, status);
+    contour_kernel<<<grid, 32, small_smem, st>>>(bits, bbox, select, n, h, wpm, need_large ? (large_ok ? 1 : 0) : 1, max_pts, out_xy, out_count, status);
     NUHTC_LAUNCH_CHECK();
     if (large_ok) {
         NUHTC_CUDA(cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_smem));
         const unsigned g2 = (unsigned)(n < (int64_t)nuhtc_sm_count() * 2 ? n : (int64_t)nuhtc_sm_count() * 2);
-        contour_kernel<<<g2, 32, large_smem, st>>>(bits, bbox, n, h, wpm, 2, max_pts, out_xy, out_count, status);
+        contour_kernel<<<g2, 32, large_smem, st>>>(bits, bbox, select, n, h, wpm, 2, max_pts, out_xy, out_count, status);
         NUHTC_LAUNCH_CHECK();
     }
     return NUHTC_OK;

@@ -125,7 +125,28 @@ __global__ void tile_filter_kernel(const float *__restrict__ det_boxes, const in
     tile_ids[i] = ok ? det_tile[i] : -1;
 }
 
+__global__ void keep_flags_kernel(const int32_t *__restrict__ keep, const int32_t *__restrict__ tile_start,
+                                  const int32_t *__restrict__ tile_count, int T, int max_tile, uint8_t *__restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * max_tile) return;
+    const int t = i / max_tile, r = i - t * max_tile;
+    if (r < tile_count[t]) flags[keep[tile_start[t] + r]] = 1;
+}
+
 } // namespace
+
+NUHTC_API int nuhtc_keep_flags(const int32_t *keep, const int32_t *tile_start, const int32_t *tile_count, int num_tiles,
+                               int max_tile_size, int64_t n, uint8_t *flags, void *stream) {
+    NUHTC_CHECK_ARG(num_tiles >= 1 && max_tile_size >= 1 && n >= 0, "keep_flags: bad sizes");
+    if (n == 0) return NUHTC_OK;
+    NUHTC_CHECK_ARG(keep && tile_start && tile_count && flags, "keep_flags: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    NUHTC_CUDA(cudaMemsetAsync(flags, 0, (size_t)n, st));
+    const int tot = num_tiles * max_tile_size;
+    keep_flags_kernel<<<(tot + 255) / 256, 256, 0, st>>>(keep, tile_start, tile_count, num_tiles, max_tile_size, flags);
+    NUHTC_LAUNCH_CHECK();
+    return NUHTC_OK;
+}
 
 NUHTC_API int nuhtc_delta2bbox(const float *rois, int with_batch, const float *deltas, int64_t K, const float *means,
                                const float *stds, int max_h, int max_w, double wh_ratio_clip, float divide_by, float *out,

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["delta2bbox", "multiclass_candidates", "detection_slots", "tile_filter"]
+__all__ = ["delta2bbox", "multiclass_candidates", "detection_slots", "tile_filter", "keep_flags"]
 
 _F4 = ctypes.c_float * 4
 
@@ -99,3 +99,14 @@ def tile_filter(det_boxes: torch.Tensor, area: torch.Tensor, det_tile: torch.Ten
     L.check(rc, "nuhtc_tile_filter")
     L.count("glue")
     return out
+
+
+def keep_flags(keep: torch.Tensor, tile_start: torch.Tensor, tile_count: torch.Tensor, max_tile_size: int, n: int) -> torch.Tensor:
+    """uint8 [n]: 1 for the masks listed in the mask-NMS keep lists, 0 elsewhere (infer_wsi.py:527-531 selection)."""
+    flags = torch.empty((n,), dtype=torch.uint8, device=keep.device)
+    with torch.cuda.device(keep.device):
+        rc = L.lib().nuhtc_keep_flags(keep.data_ptr(), tile_start.data_ptr(), tile_count.data_ptr(), tile_start.numel(),
+                                      int(max_tile_size), n, flags.data_ptr(), L.stream_ptr(keep.device))
+    L.check(rc, "nuhtc_keep_flags")
+    L.count("glue")
+    return flags

@@ -197,7 +197,8 @@ def nms_groups(boxes: torch.Tensor, scores: torch.Tensor, labels: Optional[torch
     """Batched greedy NMS over independent groups (images), no host sync.
 
     ``num_classes`` > 0 sorts into (group, class) segments (labels < num_classes): same result, 5x less work for 5
-    classes.  With mode 'offset' that requires non-negative box coordinates (status 3 otherwise, see the header).
+    classes; ``max_group_size`` then is the capacity of one (group, class) segment (the group's own size always works but
+    sizes the pair matrix for it).  With mode 'offset' that requires non-negative box coordinates (status 3 otherwise, see the header).
 
     Returns (keep [N] int64, group_start [G] int64, group_count [G] int64, status [1] int32), all on the device:
     group g's kept original indices, score-descending, are keep[group_start[g] : group_start[g]+group_count[g]]."""

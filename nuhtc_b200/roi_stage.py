@@ -70,7 +70,7 @@ class RoIStageResult:
     det_valid: Optional[torch.Tensor] = None   # [D] bool: D = B*max_per_img slots, tile-major; invalid slots are padding
     det_cand: Optional[torch.Tensor] = None    # [D] int64 candidate id (roi*num_classes + label) of each slot
     status: Optional[tuple] = None             # device status words of the NMS / mask-NMS (/ contour) launches
-    contour_xy: Optional[torch.Tensor] = None  # [D,contour_max_pts,2] int32 tile-frame contour points (cfg.contour_max_pts > 0)
+    contour_xy: Optional[torch.Tensor] = None  # [D,contour_max_pts,2] int32 contour points of the mask-NMS survivors (cfg.contour_max_pts > 0)
     contour_count: Optional[torch.Tensor] = None   # [D] int32
 
     def check(self) -> None:
@@ -226,7 +226,8 @@ class RoIStage:
             max_rois_per_tile = int(torch.bincount(tile_of_roi.long(), minlength=B).max().item())
         with self._t("nms"):
             # decoded boxes are clamped to the frame (max_shape), so no coordinate is negative: class segments are exact
-            keep, gstart, gcount, status = nms_groups(cand_boxes, cand_scores, cand_labels, groups, B, max_rois_per_tile * C,
+            # capacity is per (tile, class) segment: a RoI contributes one candidate per class
+            keep, gstart, gcount, status = nms_groups(cand_boxes, cand_scores, cand_labels, groups, B, max_rois_per_tile,
                                                       cfg.nms_iou, 0, "offset", num_classes=C)
         self._rec(nms_boxes=bboxes, nms_scores=scores, nms_keep=keep, nms_start=gstart, nms_count=gcount)
         # max_per_img truncation WITHOUT a host round trip: every tile gets max_per_img detection slots; slot r of tile
@@ -285,8 +286,9 @@ class RoIStage:
         cxy = ccnt = None
         stat = (status, st2)
         if cfg.contour_max_pts > 0:
-            with self._t("contours"):
-                cxy, ccnt, st3 = mask_contours(bits, W, cfg.contour_max_pts, check=False, bbox=bbox)
+            with self._t("contours"):   # only the survivors of the mask NMS are traced (infer_wsi.py:527-529)
+                sel = det_ops.keep_flags(keep2, tstart, tcount, cap, D)
+                cxy, ccnt, st3 = mask_contours(bits, W, cfg.contour_max_pts, check=False, bbox=bbox, select=sel)
             stat = (status, st2, st3)
         if side is not None:
             torch.cuda.current_stream(dev).wait_stream(side)

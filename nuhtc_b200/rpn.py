@@ -93,7 +93,7 @@ def proposals_batched(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[t
     min_bbox_size = _cfg_get(cfg, "min_bbox_size", -1)
     L = len(cls_scores)
     boxes, scores, labels, groups = [], [], [], []
-    per_image = 0
+    per_image = per_level = 0
     for b in range(B):
         n_b = 0
         for l in range(L):
@@ -103,6 +103,7 @@ def proposals_batched(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[t
             labels.append(s.new_full((s.numel(),), l, dtype=torch.long))
             groups.append(torch.full((s.numel(),), b, dtype=torch.int32, device=s.device))
             n_b += s.numel()
+            per_level = max(per_level, s.numel())
         per_image = max(per_image, n_b)
     boxes, scores, labels, groups = torch.cat(boxes), torch.cat(scores), torch.cat(labels), torch.cat(groups)
     if min_bbox_size >= 0:
@@ -110,7 +111,7 @@ def proposals_batched(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[t
         groups = torch.where(ok, groups, torch.full_like(groups, -1))
     split_thr = nms_cfg.pop("split_thr", 10000)
     mode = "offset" if per_image < split_thr else "perclass"  # NB: mmcv decides on the per-image candidate count AFTER the size filter
-    keep, gstart, gcount, status = nms_groups(boxes, scores, labels, groups, B, per_image, iou_thr, 0, mode, num_classes=L)
+    keep, gstart, gcount, status = nms_groups(boxes, scores, labels, groups, B, per_level, iou_thr, 0, mode, num_classes=L)
     host = torch.stack([gstart, torch.clamp(gcount, max=max_per_img)]).cpu()
     if int(status.item()) != 0:
         raise RuntimeError(f"rpn nms status {int(status.item())}")

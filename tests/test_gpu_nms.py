@@ -150,6 +150,15 @@ def test_class_segmented_nms_equals_all_pairs(oracle):
         idx = (Gp == g).nonzero().squeeze(1)
         _, k_ref = oracle.batched_nms(B[idx], S[idx], Lb[idx], dict(type="nms", iou_threshold=0.5))
         assert torch.equal(b.cpu(), idx[k_ref]), g
+    # the capacity of the segmented form is per (group, class) list: the tight bound gives the same lists, one less is flagged
+    ok = Gp >= 0
+    seg_max = int(torch.bincount((Gp[ok].long() * 5 + Lb[ok]), minlength=G * 5).max())
+    k2, s2, c2, st2 = nb.nms_groups(B.cuda(), S.cuda(), Lb.cuda(), Gp.cuda(), G, seg_max, 0.5, 0, "offset", num_classes=5)
+    assert int(st2.item()) == 0 and torch.equal(c2, c1)
+    for g in range(G):
+        assert torch.equal(k2[s2[g]: s2[g] + c2[g]], k1[s1[g]: s1[g] + c1[g]])
+    _, _, _, st3 = nb.nms_groups(B.cuda(), S.cuda(), Lb.cuda(), Gp.cuda(), G, seg_max - 1, 0.5, 0, "offset", num_classes=5)
+    assert int(st3.item()) == 1
     Bn = B.clone()
     Bn[int((Gp >= 0).nonzero()[3])] -= 4000.0
     _, _, _, st = nb.nms_groups(Bn.cuda(), S.cuda(), Lb.cuda(), Gp.cuda(), G, 1200, 0.5, 0, "offset", num_classes=5)
