@@ -39,3 +39,30 @@ def test_synth_shapes_and_levels(oracle):
     d = synth.slide_nuclei(3, 2, per_tile=5)
     assert d["voff"][-1] == d["xy"].shape[0] and len(np.unique(d["score"])) == len(d["score"])
     assert (np.diff(d["voff"]) >= 3).all()
+
+
+def test_tile_features_wire_format_and_sidecar(tmp_path):
+    """QuPath Feature dicts of tools/infer_wsi.py:541-585 and the binary sidecar round trip (host logic, no GPU)."""
+    import json
+    from nuhtc_b200.contours import read_sidecar, tile_features, write_sidecar
+    ring_xy = np.array([[10, 20], [10, 24], [15, 24], [15, 20], [10, 20], [100, 7], [103, 9], [101, 12], [100, 7]], dtype=np.float64)
+    voff = np.array([0, 5, 9], dtype=np.int64)
+    boxes = np.array([[10, 20, 16, 25], [100, 7, 104, 13]], dtype=np.float64)
+    labels, scores = np.array([2, 0]), np.array([0.91, 0.42], dtype=np.float32)
+    classes = ("a", "b", "c")
+    colors = ([255, 0, 0], [0, 255, 0], [0, 0, 255])
+    geo, pts = tile_features(ring_xy, voff, boxes, labels, scores, classes, colors)
+    json.dumps(geo), json.dumps(pts)                                      # plain python types only
+    assert geo[0]["geometry"] == {"type": "Polygon", "coordinates": [[[10, 20], [10, 24], [15, 24], [15, 20], [10, 20]]]}
+    assert geo[0]["properties"] == {"objectType": "annotation", "label": 2, "score": float(np.float32(0.91)),
+                                    "classification": {"name": "c", "color": [0, 0, 255]}, "isLocked": False}
+    assert pts[1]["geometry"] == {"type": "Point", "coordinates": [102.0, 10.0]}
+    # the flat feature list is what nuclei_merge reads back
+    from nuhtc_b200.nuclei_merge import features_to_arrays
+    xy2, voff2, sc2 = features_to_arrays(geo)
+    assert np.array_equal(xy2, ring_xy) and np.array_equal(voff2, voff) and np.allclose(sc2, scores)
+    path = str(tmp_path / "nuclei.npz")
+    write_sidecar(path, ring_xy, voff, scores, labels, boxes)
+    xy3, voff3, sc3, lab3, bb3 = read_sidecar(path)
+    assert np.array_equal(xy3, ring_xy) and np.array_equal(voff3, voff) and np.array_equal(lab3, labels)
+    assert np.allclose(sc3, scores) and np.allclose(bb3, boxes)
