@@ -61,7 +61,8 @@ def parse():
 def stage_config(args):
     from nuhtc_b200.roi_stage import RoIStageConfig
     return RoIStageConfig(extractor="single", bbox_sampling_ratio=0, mask_sampling_ratio=0, score_thr=0.05, nms_iou=0.5,
-                          max_per_img=args.max_per_img, dense_masks=(args.lane == "dense"), contour_max_pts=256)
+                          max_per_img=args.max_per_img, dense_masks=(args.lane == "dense"), contour_max_pts=256,
+                          fused_dense_bits=os.environ.get("NUHTC_STAGE_FUSED_PASTE", "1") != "0")
 
 
 def workload_name(args):
@@ -414,7 +415,8 @@ def run_ours(args):
     D = int(res.det_boxes.shape[0])
     extra = {}
     if paste:
-        pbytes = D * (256 * 256 * (1 if args.lane == "dense" else 0.125) + 28 * 28 * 4 + 16)
+        # dense frame (+ the bit rows when both come from the one-evaluation kernel) + the 28x28 map + the box
+        pbytes = D * (256 * 256 * (1 if args.lane == "dense" else 0.125) + (256 * 256 // 8 if cfg.fused_dense_bits else 0) + 28 * 28 * 4 + 16)
         pms = float(np.mean(paste))
         extra["paste"] = {"achieved": pbytes / (pms * 1e-3) / 1e9, "unit": "GB/s", "frac": pbytes / (pms * 1e-3) / 1e9 / peak,
                           "algorithmic_bytes_per_launch": pbytes, "avg_launch_ms": pms, "masks_per_launch": D}

@@ -137,6 +137,10 @@ int nuhtc_nms(const float *boxes, const float *scores, const int64_t *labels, co
 #define NUHTC_PASTE_BITS 2
 int nuhtc_paste_masks(const float *probs, const float *boxes, int N, int mh, int mw, int img_h, int img_w,
                       float thr, int out_kind, void *out, int32_t *area, int32_t *bbox, void *stream);
+/* Both binary forms from ONE evaluation of every mask (img_w % 16 == 0): dense uint8 [N,img_h,img_w] (what
+ * get_seg_masks returns) and the bit rows [N,img_h,ceil(img_w/64)] the mask NMS / contour kernels read. */
+int nuhtc_paste_masks_dense_bits(const float *probs, const float *boxes, int N, int mh, int mw, int img_h, int img_w,
+                                 float thr, uint8_t *dense, uint64_t *bits, int32_t *area, int32_t *bbox, void *stream);
 
 /* ---- per-tile mask NMS -----------------------------------------------------------------------
  * Replaces `mask_nms(masks, pred_scores, thr)` of tools/infer_wsi.py:60-84 (pycocotools

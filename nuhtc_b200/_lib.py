@@ -36,6 +36,7 @@ SIGNATURES = {
     "nuhtc_nms_workspace_bytes": (_sz, [_i64, _i, _i64, _i]),
     "nuhtc_nms": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i64, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_paste_masks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
+    "nuhtc_paste_masks_dense_bits": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "nuhtc_pack_masks": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "nuhtc_mask_nms_workspace_bytes": (_sz, [_i, _i, _i]),
     "nuhtc_mask_nms": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -98,7 +99,7 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
 # ---- launch accounting: how many of OUR kernels each C-ABI call enqueues (bench.py reports the sum as
 # "gpu_launches"; library kernels such as cub's radix sort are not counted)
 LAUNCHES = {"n": 0}
-KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "attention_pool": 4, "roi_align": 1, "nms": 7, "paste": 2, "pack": 3, "mask_nms": 6, "merge": 16, "contours": 2, "rings": 1, "glue": 1}
+KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "attention_pool": 4, "roi_align": 1, "nms": 7, "paste": 2, "paste_dual": 1, "pack": 3, "mask_nms": 6, "merge": 16, "contours": 2, "rings": 1, "glue": 1}
 
 
 def count(op: str, n: int = 1) -> None:

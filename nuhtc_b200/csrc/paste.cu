@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256) fill_zero_kernel(uint4 *__restrict__ p, s
 template <int KIND, bool FUSE_FILL = false>
 __global__ void __launch_bounds__(kPasteThreads) paste_sparse_kernel(const float *__restrict__ probs, const float *__restrict__ boxes,
                                                                      int mh, int mw, int H, int W, float thr, void *__restrict__ outv,
-                                                                     int32_t *__restrict__ area, int32_t *__restrict__ bbox) {
+                                                                     int32_t *__restrict__ area, int32_t *__restrict__ bbox,
+                                                                     unsigned long long *__restrict__ bits2 = nullptr) {
     __shared__ float s_m[kMaxMaskElems];
     __shared__ int s_red[5][kPasteThreads / 32];
     const int n = blockIdx.x, tid = threadIdx.x;
@@ -121,6 +122,13 @@ __global__ void __launch_bounds__(kPasteThreads) paste_sparse_kernel(const float
         for (int i = tid; i < nseg; i += kPasteThreads) {
             const int y = i / spr, sx = i - y * spr;
             if (!(any && y >= ay0 && y < ay1 && sx >= s0 && sx < s1)) st_stream_u4(frame + (size_t)i * 16, z);
+        }
+        if (bits2) { // second output of the same evaluation: the bit rows.  Zeroed whole first, then every 16-pixel segment of
+                     // the reachable rectangle stores its own 16 bits (bit x % 64 of word x / 64 = the uint16 at byte x / 8)
+            uint4 *bf = reinterpret_cast<uint4 *>(bits2 + (size_t)n * H * ((W + 63) / 64));
+            const int n16 = H * ((W + 63) / 64) / 2;
+            for (int i = tid; i < n16; i += kPasteThreads) bf[i] = z;
+            __syncthreads();
         }
     }
     if (any) { // uniform over the CTA
@@ -195,6 +203,13 @@ __global__ void __launch_bounds__(kPasteThreads) paste_sparse_kernel(const float
                             }
                         }
                         st_stream_u4(outb + seg * 16, make_uint4(w[0], w[1], w[2], w[3]));
+                        if (FUSE_FILL && bits2) {
+                            uint32_t b16 = 0u;
+#pragma unroll
+                            for (int u = 0; u < PX; ++u) b16 |= ((w[u >> 2] >> (8 * (u & 3))) & 1u) << u;
+                            reinterpret_cast<uint16_t *>(bits2 + (size_t)n * H * ((W + 63) / 64))[((size_t)y * ((W + 63) / 64) * 64 + xs) / 16] =
+                                (uint16_t)b16;
+                        }
                     } else {
                         st_stream_f4((float *)outb + seg * 4, make_float4(v[0], v[1], v[2], v[3]));
                     }
@@ -258,6 +273,20 @@ __global__ void __launch_bounds__(kPasteThreads) paste_sparse_kernel(const float
 }
 
 } // namespace
+
+NUHTC_API int nuhtc_paste_masks_dense_bits(const float *probs, const float *boxes, int N, int mh, int mw, int img_h, int img_w,
+                                           float thr, uint8_t *dense, uint64_t *bits, int32_t *area, int32_t *bbox, void *stream) {
+    NUHTC_CHECK_ARG(N >= 0 && mh >= 1 && mw >= 1 && img_h >= 1 && img_w >= 1, "paste: bad sizes");
+    NUHTC_CHECK_ARG(mh * mw <= kMaxMaskElems, "paste: mask %dx%d larger than the staged maximum", mh, mw);
+    NUHTC_CHECK_ARG(img_w % 16 == 0 && (img_h * ((img_w + 63) / 64)) % 2 == 0, "paste_dense_bits: img_w must be a multiple of 16");
+    if (N == 0) return NUHTC_OK;
+    NUHTC_CHECK_ARG(probs && boxes && dense && bits, "paste: null pointer");
+    NUHTC_CHECK_ARG(((uintptr_t)dense) % 16 == 0 && ((uintptr_t)bits) % 16 == 0, "paste: outputs must be 16-byte aligned");
+    paste_sparse_kernel<NUHTC_PASTE_BIN, true><<<N, kPasteThreads, 0, (cudaStream_t)stream>>>(
+        probs, boxes, mh, mw, img_h, img_w, thr, dense, area, bbox, (unsigned long long *)bits);
+    NUHTC_LAUNCH_CHECK();
+    return NUHTC_OK;
+}
 
 NUHTC_API int nuhtc_paste_masks(const float *probs, const float *boxes, int N, int mh, int mw, int img_h, int img_w, float thr,
                                 int out_kind, void *out, int32_t *area, int32_t *bbox, void *stream) {

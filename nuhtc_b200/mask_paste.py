@@ -14,7 +14,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["_do_paste_mask", "paste_masks", "get_seg_masks", "get_seg_masks_device"]
+__all__ = ["paste_masks_dense_bits", "_do_paste_mask", "paste_masks", "get_seg_masks", "get_seg_masks_device"]
 
 
 def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int, thr: Optional[float] = None,
@@ -60,6 +60,33 @@ def paste_masks(masks: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int
         L.check(rc, "paste_masks")
         L.count("paste")
     return (out, area, bbox) if want_stats else out
+
+
+def paste_masks_dense_bits(masks: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int, thr: float):
+    """Dense bool frames AND bit rows (+ area, tight box) from one evaluation of every mask (img_w % 16 == 0):
+    returns (dense bool [N,H,W], bits int64 [N,H,ceil(W/64)], area int32 [N], bbox int32 [N,4])."""
+    L.require_cuda(masks, "masks")
+    L.require_cuda(boxes, "boxes")
+    if masks.dim() == 4:
+        assert masks.size(1) == 1, "class-agnostic mask [N,1,h,w] expected (select the label channel first)"
+        masks = masks[:, 0]
+    N, mh, mw = masks.shape
+    dev = masks.device
+    masks = masks.to(torch.float32).contiguous()
+    boxes = boxes[:, :4].to(torch.float32).contiguous()
+    img_h, img_w = int(img_h), int(img_w)
+    dense = torch.empty((N, img_h, img_w), dtype=torch.bool, device=dev)
+    bits = torch.empty((N, img_h, (img_w + 63) // 64), dtype=torch.int64, device=dev)
+    area = torch.empty(N, dtype=torch.int32, device=dev)
+    bbox = torch.empty((N, 4), dtype=torch.int32, device=dev)
+    if N:
+        with torch.cuda.device(dev):
+            rc = L.lib().nuhtc_paste_masks_dense_bits(masks.data_ptr(), boxes.data_ptr(), N, mh, mw, img_h, img_w, float(thr),
+                                                      dense.data_ptr(), bits.data_ptr(), area.data_ptr(), bbox.data_ptr(),
+                                                      L.stream_ptr(dev))
+        L.check(rc, "paste_masks_dense_bits")
+        L.count("paste_dual")
+    return dense, bits, area, bbox
 
 
 def _do_paste_mask(masks: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int, skip_empty: bool = True):

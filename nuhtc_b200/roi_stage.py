@@ -21,7 +21,7 @@ import torch
 from . import det_ops
 from .contours import mask_contours
 from .mask_nms import mask_nms_device
-from .mask_paste import paste_masks
+from .mask_paste import paste_masks, paste_masks_dense_bits
 from .mmcv_ops import nms_groups, roi_align_levels
 
 __all__ = ["RoIStageConfig", "RoIStage", "RoIStageResult", "delta2bbox", "bbox2roi"]
@@ -47,6 +47,7 @@ class RoIStageConfig:
     img_shape: Tuple[int, int] = (512, 512)   # network frame (tile x scale_factor)
     ori_shape: Tuple[int, int] = (256, 256)   # tile frame
     scale_factor: float = 2.0
+    fused_dense_bits: bool = True      # dense frames + bit rows from one evaluation (needs W % 16 == 0)
     overlap_dense_paste: bool = True   # write the dense masks on a forked stream beside the mask NMS / contour kernels
     contour_max_pts: int = 0           # > 0: trace mask2inst contours of every detection slot (tools/infer_wsi.py:528)
     margin: int = 0                    # tools/infer_wsi.py --margin
@@ -258,22 +259,27 @@ class RoIStage:
         # the bit rows (+ area / tight box) feed the mask NMS; the dense uint8 frames are what get_seg_masks returns.
         # Both come straight from the 28x28 maps: re-reading 64 KB per nucleus to pack it would cost more than
         # evaluating its ~1e3 reachable pixels twice.
-        with self._t("paste_bits"):
-            bits, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bits", want_stats=True)
-        # the dense frames are an output only (mask NMS and contours read the bit rows), and writing them is pure HBM
-        # traffic while the mask NMS scan and the contour walk are latency bound: they run side by side on a forked stream
         masks = None
         side = None
-        if cfg.dense_masks:
-            main = torch.cuda.current_stream(dev)
-            if cfg.overlap_dense_paste and not (self.timer is not None and getattr(self.timer, 'enabled', True)):  # per-op timing keeps one stream
-                side = self._side_stream(dev)
-                side.wait_stream(main)
-            with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-                with self._t("paste"):
-                    masks = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bin")
-            if side is not None:
-                masks.record_stream(main)
+        if cfg.dense_masks and cfg.fused_dense_bits and W % 16 == 0:
+            # one evaluation of every mask writes the dense frame (each byte once) and the bit rows
+            with self._t("paste"):
+                masks, bits, area, bbox = paste_masks_dense_bits(probs, det_boxes, H, W, cfg.mask_thr_binary)
+        else:
+            with self._t("paste_bits"):
+                bits, area, bbox = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bits", want_stats=True)
+            # the dense frames are an output only (mask NMS and contours read the bit rows), and writing them is pure HBM
+            # traffic while the mask NMS scan and the contour walk are latency bound: they run side by side on a forked stream
+            if cfg.dense_masks:
+                main = torch.cuda.current_stream(dev)
+                if cfg.overlap_dense_paste and not (self.timer is not None and getattr(self.timer, 'enabled', True)):  # per-op timing keeps one stream
+                    side = self._side_stream(dev)
+                    side.wait_stream(main)
+                with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                    with self._t("paste"):
+                        masks = paste_masks(probs, det_boxes, H, W, thr=cfg.mask_thr_binary, kind="bin")
+                if side is not None:
+                    masks.record_stream(main)
         self._rec(paste_probs=probs, paste_boxes=det_boxes)
 
         # tools/infer_wsi.py:510-521 margin / min_area filter, then per-tile mask NMS (:526)

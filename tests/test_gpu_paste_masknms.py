@@ -131,3 +131,20 @@ def test_mask_nms_odd_width_and_tiles(oracle):
         idx = np.nonzero(Tt == t)[0]
         ref = idx[oracle.mask_nms(M[idx], S[idx], thr=0.05)]
         assert (keep[tstart[t]: tstart[t] + tcount[t]] == ref).all()
+
+
+def test_dense_and_bits_from_one_evaluation():
+    """nuhtc_paste_masks_dense_bits == the two single-output calls (frames, bit rows, area, tight boxes)."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    from nuhtc_b200.mask_paste import paste_masks_dense_bits
+    boxes, probs, _ = synth.nuclei_masks(300, frame=256, seed=21)
+    boxes[0] = torch.tensor([-50.0, -50.0, -20.0, -10.0])      # outside
+    boxes[1] = torch.tensor([200.0, 180.0, 300.0, 290.0])      # clipped
+    boxes[2] = torch.tensor([0.0, 0.0, 256.0, 256.0])          # whole frame
+    for thr in (0.5, 0.0):
+        dense, bits, area, bbox = paste_masks_dense_bits(probs.cuda(), boxes.cuda(), 256, 256, thr)
+        d1, a1, b1 = nb.paste_masks(probs.cuda(), boxes.cuda(), 256, 256, thr=thr, kind="bin", want_stats=True)
+        w1, a2, b2 = nb.paste_masks(probs.cuda(), boxes.cuda(), 256, 256, thr=thr, kind="bits", want_stats=True)
+        assert torch.equal(dense, d1) and torch.equal(bits, w1)
+        assert torch.equal(area, a1) and torch.equal(area, a2) and torch.equal(bbox, b1) and torch.equal(bbox, b2)
