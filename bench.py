@@ -184,6 +184,16 @@ class EventTimers:
         return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.pairs.items()}
 
 
+def trimmed_mean(v):
+    """Mean of the samples within 3x the median: an eager step now and then pays a cudaMalloc / lazy-load stall on the host
+    that lands inside an event bracket (the GPU idles meanwhile); those are not kernel time."""
+    v = np.asarray(v, dtype=np.float64)
+    if v.size == 0:
+        return None, 0
+    keep = v[v <= 3.0 * np.median(v)]
+    return float(keep.mean()), int(v.size - keep.size)
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -369,8 +379,8 @@ def run_ours(args):
 
     # ---- per-kernel durations (CUDA events cannot bracket nodes inside a graph): the same K steps are repeated eagerly
     # with an event pair around every op; these feed `roofline`, `roofline_other` and `breakdown_ms_per_step` only
-    for _ in range(2):      # eager warm-up: the caching allocator re-creates the blocks the graph's private pool took over
-        one_step()
+    for _ in range(3):      # eager warm-up: the caching allocator re-creates the blocks the graph's private pool took over
+        res = one_step()    # (the previous result stays alive while the next step allocates, exactly like the loop below)
     torch.cuda.synchronize()
     timers.enabled = True
     timers.pairs = {}
@@ -400,7 +410,7 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     lv = sorted(set(nb_levels(rois_h)))
     ra = op_ms.get("roi_align_bbox", [])
-    ra_ms = float(np.mean(ra)) if ra else None
+    ra_ms, ra_dropped = trimmed_mean(ra)
     alg = roi_align_bytes(K, C, 7, feats_h, lv)
     roofline = None
     if ra_ms:
@@ -410,29 +420,31 @@ def run_ours(args):
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the
                     # `ncu --set full` capture summarised in profiles/r01_roialign_pipe.md (274.1 MB + 752.7 MB)
                     "traffic": 1026811136 if (K == 16000 and C == 256 and args.dist == "nuclei") else None,
-                    "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ra_ms, "launches_timed": len(ra), "peak_source": peak_src}
+                    "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ra_ms, "launches_timed": len(ra) - ra_dropped,
+                    "host_stall_samples_dropped": ra_dropped, "peak_source": peak_src}
     paste = op_ms.get("paste", [])
     D = int(res.det_boxes.shape[0])
     extra = {}
     if paste:
         # dense frame (+ the bit rows when both come from the one-evaluation kernel) + the 28x28 map + the box
         pbytes = D * (256 * 256 * (1 if args.lane == "dense" else 0.125) + (256 * 256 // 8 if cfg.fused_dense_bits else 0) + 28 * 28 * 4 + 16)
-        pms = float(np.mean(paste))
+        pms, _ = trimmed_mean(paste)
         extra["paste"] = {"achieved": pbytes / (pms * 1e-3) / 1e9, "unit": "GB/s", "frac": pbytes / (pms * 1e-3) / 1e9 / peak,
                           "algorithmic_bytes_per_launch": pbytes, "avg_launch_ms": pms, "masks_per_launch": D}
     rm = op_ms.get("roi_align_mask", [])
     if rm:
         mbytes = roi_align_bytes(D, C, 14, feats_h, lv)
-        mms = float(np.mean(rm))
+        mms, _ = trimmed_mean(rm)
         extra["roi_align_mask"] = {"achieved": mbytes / (mms * 1e-3) / 1e9, "unit": "GB/s", "frac": mbytes / (mms * 1e-3) / 1e9 / peak,
                                    "algorithmic_bytes_per_launch": mbytes, "avg_launch_ms": mms}
     tr = op_ms.get("nchw_to_nhwc", [])
     if tr:
         tbytes = 2 * sum(f.numel() * 4 for f in feats_h)
-        tms = float(np.mean(tr))
+        tms, _ = trimmed_mean(tr)
         extra["nchw_to_nhwc"] = {"achieved": tbytes / (tms * 1e-3) / 1e9, "unit": "GB/s", "frac": tbytes / (tms * 1e-3) / 1e9 / peak,
                                  "avg_launch_ms": tms}
-    breakdown = {k: float(np.sum(v)) / args.steps for k, v in op_ms.items()}
+    # per step: (trimmed) mean bracket x brackets per step
+    breakdown = {k: trimmed_mean(v)[0] * len(v) / args.steps for k, v in op_ms.items() if len(v)}
 
     # ---- e2e: pinned host inputs copied every step, results read back every step
     e2e = None
@@ -463,7 +475,8 @@ def run_ours(args):
                 "timing": {"timed_region": ("cuda graph replay of the captured step" + (f", {len(lanes)} batches in flight on {len(lanes)} streams"
                                                                                           if lanes else "")) if graph is not None else "eager",
                            "eager_instrumented_ms_per_step": eager_ms / args.steps,
-                           "per_kernel_numbers": "CUDA events around every op in an eager repeat of the same steps, right after the timed region"},
+                           "per_kernel_numbers": "CUDA events around every op in an eager repeat of the same steps, right after the timed region; "
+                                                 "brackets above 3x their median (host stalls of the eager loop) are left out of the means"},
                 "cpu_baseline": cpu,
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches}
         print(json.dumps(line), flush=True)
