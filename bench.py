@@ -73,18 +73,21 @@ def workload_name(args):
 
 class ClockSampler:
     """SM clock / throttle reasons of this rank's GPU sampled DURING the timed region.  NVML in-process (initialised before
-    the timed region, one light query every 2 ms from a thread); a per-rank `nvidia-smi -lms` subprocess takes about a second
+    the timed region, one light query every 10 ms from a thread, rank 0 only); a per-rank `nvidia-smi -lms` subprocess takes about a second
     to start and holds driver locks while it does, which on an 8-GPU box stalled the launches of the very region it was
     meant to observe.  Falls back to nvidia-smi when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index = index
         self.lines = []
         self.proc = None
         self.nvml = None
         self.stop = threading.Event()
+        self.enabled = enabled
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -110,9 +113,11 @@ class ClockSampler:
                 self.lines.append(f"{self.index},{sm},{self.max_sm},0,0,{flags}")
             except Exception:
                 pass
-            self.stop.wait(0.002)
+            self.stop.wait(0.010)   # an NVML query takes driver locks: polling faster slows the host side of the merge down
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         if self.nvml is not None:
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
@@ -340,7 +345,7 @@ def run_ours(args):
     lanes = [torch.cuda.Stream() for _ in range(max(1, args.inflight))] if (graph is not None and args.inflight > 1) else []
 
     # ---- timed region: exactly K steps + the one merge
-    sampler = ClockSampler(local)   # NVML is initialised here, outside the timed region
+    sampler = ClockSampler(local, enabled=(rank == 0))   # NVML is initialised here, outside the timed region
     _lib.LAUNCHES["n"] = 0
     if world > 1:
         dist.barrier()
