@@ -13,7 +13,7 @@ from typing import List, Sequence
 import torch
 
 from .mmcv_ops import batched_nms, nms_groups
-from .roi_stage import delta2bbox
+from .det_ops import delta2bbox
 
 __all__ = ["get_bboxes_single", "bbox_post_process", "proposals_batched"]
 
@@ -46,7 +46,7 @@ def bbox_post_process(mlvl_scores, mlvl_bboxes, mlvl_valid_anchors, level_ids, c
     scores = torch.cat(mlvl_scores)
     anchors = torch.cat(mlvl_valid_anchors)
     rpn_bbox_pred = torch.cat(mlvl_bboxes)
-    proposals = delta2bbox(anchors, rpn_bbox_pred, (1., 1., 1., 1.), max_shape=img_shape)
+    proposals = delta2bbox(anchors.contiguous(), rpn_bbox_pred.contiguous(), stds=(1., 1., 1., 1.), max_shape=img_shape)
     ids = torch.cat(level_ids)
     min_bbox_size = _cfg_get(cfg, "min_bbox_size", -1)
     if min_bbox_size >= 0:
@@ -92,20 +92,39 @@ def proposals_batched(cls_scores: Sequence[torch.Tensor], bbox_preds: Sequence[t
     max_per_img = _cfg_get(cfg, "max_per_img")
     min_bbox_size = _cfg_get(cfg, "min_bbox_size", -1)
     L = len(cls_scores)
+    dev = cls_scores[0].device
     boxes, scores, labels, groups = [], [], [], []
     per_image = per_level = 0
-    for b in range(B):
-        n_b = 0
-        for l in range(L):
-            s, d, a = _level_topk(cls_scores[l][b], bbox_preds[l][b], mlvl_anchors[l], nms_pre, use_sigmoid_cls)
-            boxes.append(delta2bbox(a, d, (1., 1., 1., 1.), max_shape=img_shape))
-            scores.append(s)
-            labels.append(s.new_full((s.numel(),), l, dtype=torch.long))
-            groups.append(torch.full((s.numel(),), b, dtype=torch.int32, device=s.device))
-            n_b += s.numel()
-            per_level = max(per_level, s.numel())
-        per_image = max(per_image, n_b)
-    boxes, scores, labels, groups = torch.cat(boxes), torch.cat(scores), torch.cat(labels), torch.cat(groups)
+    img = torch.arange(B, device=dev, dtype=torch.int32)
+    for l in range(L):   # one sort / gather / decode per LEVEL for the whole batch (the reference loops images x levels)
+        cs = cls_scores[l].permute(0, 2, 3, 1)
+        if use_sigmoid_cls:
+            s = cs.reshape(B, -1).sigmoid()
+        else:
+            s = cs.reshape(B, -1, 2).softmax(dim=2)[:, :, 0]
+        d = bbox_preds[l].permute(0, 2, 3, 1).reshape(B, -1, 4)
+        a = mlvl_anchors[l]
+        n = s.shape[1]
+        if 0 < nms_pre < n:
+            s, idx = s.sort(dim=1, descending=True)
+            s, idx = s[:, :nms_pre], idx[:, :nms_pre]
+            d = torch.gather(d, 1, idx[:, :, None].expand(B, nms_pre, 4))
+            a = a[idx]                                                   # [B,k,4]
+        else:
+            a = a[None].expand(B, n, 4)
+        k = s.shape[1]
+        boxes.append(delta2bbox(a.reshape(-1, 4).contiguous(), d.reshape(-1, 4).contiguous(), stds=(1., 1., 1., 1.),
+                                max_shape=img_shape).view(B, k, 4))
+        scores.append(s)
+        labels.append(torch.full((B, k), l, dtype=torch.long, device=dev))
+        groups.append(img[:, None].expand(B, k))
+        per_image += k
+        per_level = max(per_level, k)
+    # image-major order: the NMS breaks score ties by index, like the per-image call on the level-concatenated candidates
+    boxes = torch.cat(boxes, 1).reshape(-1, 4)
+    scores = torch.cat(scores, 1).reshape(-1)
+    labels = torch.cat(labels, 1).reshape(-1)
+    groups = torch.cat(groups, 1).reshape(-1).contiguous()
     if min_bbox_size >= 0:
         ok = ((boxes[:, 2] - boxes[:, 0]) > min_bbox_size) & ((boxes[:, 3] - boxes[:, 1]) > min_bbox_size)
         groups = torch.where(ok, groups, torch.full_like(groups, -1))

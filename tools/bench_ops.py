@@ -113,6 +113,33 @@ def main():
             cfg = dict(type="nms", iou_threshold=0.5)
             ms, best = timeit(lambda: nb.batched_nms(b_, s_, l_, cfg), iters=5, warm=2)
             rec(f"batched_nms_{N}", ms, best, N * 28, boxes_per_s=round(N / ms * 1e3))
+    if want("attention"):
+        # AttentionRoIExtractor (PanNuke config): C = 64, levels 2,3 of a 512 px frame, K = 16000 RoIs
+        f64 = [f.to(dev) for f in synth.fpn_levels(B, 64)]
+        r_ = synth.proposals(B, 1000, "nuclei").to(dev)
+        for lvl in (2, 3):
+            ms, best = timeit(lambda: nb.mmcv_ops.attention_pool(f64[lvl], r_, float(synth.FPN_STRIDES[lvl]), 0.0))
+            hw = f64[lvl].shape[2] * f64[lvl].shape[3]
+            rec(f"attention_pool_level{lvl}_C64", ms, best, f64[lvl].numel() * 4 + r_.shape[0] * (20 + 256),
+                gflops=round(4 * 64 * hw * r_.shape[0] / ms / 1e6, 1))
+    if want("rpn"):
+        from nuhtc_b200 import rpn
+        g = torch.Generator().manual_seed(0)
+        cls, reg, anc = [], [], []
+        for s_ in (4, 8, 16, 32):
+            h_ = 512 // s_
+            cls.append((torch.randn(B, 3, h_, h_, generator=g) * 2).to(dev))
+            reg.append((torch.randn(B, 12, h_, h_, generator=g) * 0.25).to(dev))
+            ys, xs = torch.meshgrid(torch.arange(h_), torch.arange(h_), indexing="ij")
+            ctr = torch.stack([xs, ys], -1).reshape(-1, 1, 2).float() * s_
+            wh = torch.tensor([[1.0, 1.0], [1.4, 0.7], [0.7, 1.4]]) * (4.0 * s_)
+            anc.append(torch.cat([ctr - wh / 2, ctr + wh / 2], -1).reshape(-1, 4).to(dev))
+
+        class Cfg(dict):
+            __getattr__ = dict.get
+        rcfg = Cfg(nms_pre=1000, min_bbox_size=0, nms=dict(type="nms", iou_threshold=0.7), max_per_img=1000)
+        ms, best = timeit(lambda: rpn.proposals_batched(cls, reg, anc, (512, 512, 3), rcfg), iters=5, warm=2)
+        rec(f"rpn_proposals_batched_{B}img_nms_pre1000", ms, best, B * 4000 * 28, images_per_s=round(B / ms * 1e3))
     if want("merge"):
         d = synth.slide_nuclei(64, 64, per_tile=23, seed=0)
         xy, voff, sc = (torch.from_numpy(d[k]).to(dev) for k in ("xy", "voff", "score"))
