@@ -123,3 +123,38 @@ def test_bits_lane_equals_dense_lane():
     assert torch.equal(a.tile_count, b.tile_count)
     for x, y in zip(a.kept_indices(), b.kept_indices()):
         assert torch.equal(x, y)
+
+
+def test_stage_contours_feed_the_merge(oracle):
+    """masks -> mask NMS survivors -> mask2inst contours (+ tile origin) -> cross-tile merge, all on the device, against the
+    oracle driven the way tools/infer_wsi.py:526-546 + tools/nuclei_merge.py do it (on the GPU stage's own masks)."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import det_ops
+    from nuhtc_b200.roi_stage import RoIStage
+    cfg, feats, rois, heads = _setup("single", 64, B=4, n_per=250, max_per_img=90)
+    gh = copy.copy(heads).to("cuda")
+    raw = RoIStage(cfg, gh.bbox_heads(), gh.mask_head).run([f.cuda() for f in feats], rois.cuda())
+    raw.check()
+    D = raw.det_boxes.shape[0]
+    tile_xy = torch.tensor([[0, 0], [192, 0], [0, 192], [192, 192]], dtype=torch.int32, device="cuda")   # 64 px overlap
+    origin = tile_xy[raw.det_tile.clamp(min=0).long()].contiguous()
+    sel = det_ops.keep_flags(raw.keep, raw.tile_start, raw.tile_count, cfg.max_per_img, D).bool()
+    ring, voff, index = nb.rings_for_merge(raw.contour_xy, raw.contour_count, select=sel, origin=origin)
+    assert index.numel() > 40
+    scores = raw.det_scores[index].double()
+    kept = nb.merge_arrays(ring, voff, scores, 0.05).cpu().numpy()
+    # reference flow on the CPU
+    m = raw.masks.cpu().numpy().astype(np.uint8)
+    org = origin.cpu().numpy()
+    polys, sc = [], []
+    for i in index.cpu().tolist():
+        c = oracle.mask2inst(m[i]).reshape(-1, 2) + org[i]
+        assert len(c) >= 3
+        polys.append(c.astype(np.float64))
+        sc.append(float(raw.det_scores[i]))
+    xy = np.concatenate(polys)
+    vo = np.cumsum([0] + [len(p) for p in polys]).astype(np.int64)
+    assert np.array_equal(ring.cpu().numpy(), xy) and np.array_equal(voff.cpu().numpy(), vo)
+    ref = oracle.merge_overlap_arrays(xy, vo, np.array(sc, dtype=np.float64), 0.05)
+    assert kept.tolist() == list(ref)
+    assert 0 < len(ref) < len(polys)          # some nuclei of overlapping tiles were merged away
