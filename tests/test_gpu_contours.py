@@ -104,3 +104,36 @@ def test_rings_and_mask2inst(oracle):
         ref = oracle.mask2inst(cm[i]).reshape(-1, 2) + origin[i].cpu().numpy()
         assert np.array_equal(ring[voff[k]: voff[k + 1]], ref.astype(np.float64))
     assert np.array_equal(mask2inst(cm[0]), oracle.mask2inst(cm[0]))
+
+
+def test_full_size_contour_properties():
+    """8000 nucleus masks in 256x256 frames (the bench's detection count), no oracle: every contour vertex is a set pixel,
+    a contour exists iff the mask is non-empty, and for a hole-free single blob Pick's theorem ties the traced polygon to the
+    pixel count: 2 * area(polygon) = 2 * pixels - B - 2 with B the lattice points on the polygon's edges."""
+    from nuhtc_b200 import synth, paste_masks, mask_contours
+    boxes, probs, _ = synth.nuclei_masks(8000, frame=256, seed=4)
+    bits, area, bbox = paste_masks(probs.cuda(), boxes.cuda(), 256, 256, thr=0.5, kind="bits", want_stats=True)
+    dense = paste_masks(probs.cuda(), boxes.cuda(), 256, 256, thr=0.5, kind="bin")
+    xy, cnt, _ = mask_contours(bits, 256, max_pts=256, bbox=bbox)
+    xy2, cnt2, _ = mask_contours(bits, 256, max_pts=256)                 # idempotent, with or without the tight boxes
+    assert torch.equal(cnt, cnt2)
+    assert torch.equal((cnt > 0), (area > 0))
+    n, P = xy.shape[0], xy.shape[1]
+    live = torch.arange(P, device="cuda")[None, :] < cnt[:, None]
+    assert torch.equal(xy[live], xy2[live])
+    idx = torch.arange(n, device="cuda")[:, None].expand(n, P)[live]
+    pts = xy[live].long()
+    assert dense[idx, pts[:, 1], pts[:, 0]].all()                        # vertices sit on set pixels
+    # Pick's theorem on the closed polygon
+    x = torch.where(live, xy[..., 0], torch.zeros_like(xy[..., 0])).double()
+    y = torch.where(live, xy[..., 1], torch.zeros_like(xy[..., 1])).double()
+    last = (cnt.long() - 1).clamp(min=0)
+    nxt = (torch.arange(P, device="cuda")[None, :] + 1) % P
+    xn = torch.where(torch.arange(P, device="cuda")[None, :] == last[:, None], x[:, :1], torch.gather(x, 1, nxt.expand(n, P)))
+    yn = torch.where(torch.arange(P, device="cuda")[None, :] == last[:, None], y[:, :1], torch.gather(y, 1, nxt.expand(n, P)))
+    cross = torch.where(live, x * yn - xn * y, torch.zeros_like(x)).sum(1)
+    edge_pts = torch.where(live, torch.gcd((xn - x).abs().long(), (yn - y).abs().long()), torch.zeros_like(pts.new_zeros(1)).expand(n, P)).sum(1)
+    twice_area = cross.abs().round().long()
+    ok = twice_area == 2 * area.long() - edge_pts - 2
+    big = area > 30
+    assert ok[big].float().mean().item() > 0.97                          # blobs without holes / 1-px spurs
