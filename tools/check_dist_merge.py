@@ -25,7 +25,16 @@ def main():
     slide = synth.slide_nuclei(tx, ty, per_tile=23, seed=7)
     sh = shard_by_rows(slide, rank, world)
     xy, voff, score = (torch.from_numpy(sh[k]).to(dev) for k in ("xy", "voff", "score"))
+    kept, ids = merge_distributed(xy, voff, score, sh, rank, world, 0.05, return_ids=True)   # warm-up (NCCL channels, allocator)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     kept, ids = merge_distributed(xy, voff, score, sh, rank, world, 0.05, return_ids=True)
+    e1.record()
+    torch.cuda.synchronize()
+    tms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     gids = torch.from_numpy(sh["gid"]).to(dev)[kept]
     n = torch.tensor([kept.numel()], device=dev)
     ns = [torch.zeros_like(n) for _ in range(world)]
@@ -40,9 +49,17 @@ def main():
     if rank == 0:
         allp = torch.cat([o[: int(c.item())] for o, c in zip(outs, ns)]).cpu().numpy()
         by_id = allp[np.argsort(allp[:, 1])]
-        ref = nb.merge_arrays(*(torch.from_numpy(slide[k]).to(dev) for k in ("xy", "voff", "score")), 0.05).cpu().numpy()
+        full = [torch.from_numpy(slide[k]).to(dev) for k in ("xy", "voff", "score")]
+        ref = nb.merge_arrays(*full, 0.05).cpu().numpy()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        nb.merge_arrays(*full, 0.05)
+        s1.record()
+        torch.cuda.synchronize()
         ok = len(by_id) == len(ref) and (by_id[:, 1] == np.arange(len(ref))).all() and (by_id[:, 0] == ref).all()
-        print(f"dist-merge world={world} nuclei={len(slide['score'])} kept={len(ref)} match={ok}", flush=True)
+        n_all = len(slide["score"])
+        print(f"dist-merge world={world} nuclei={n_all} kept={len(ref)} match={ok} | {world}-GPU merge {float(tms.item()):.2f} ms "
+              f"({n_all / float(tms.item()) / 1e3:.1f} M nuclei/s), single-GPU merge {s0.elapsed_time(s1):.2f} ms", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
