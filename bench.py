@@ -52,7 +52,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
-    p.add_argument("--inflight", type=int, default=2, help="batches in flight: consecutive steps alternate between this many "
+    p.add_argument("--inflight", type=int, default=3, help="batches in flight: consecutive steps alternate between this many "
                    "streams (each with its own captured graph), so the latency-bound tail of one batch (NMS scans, mask NMS, "
                    "contours) overlaps the RoIAlign of the next; 1 = strictly one step after another")
     return p.parse_args()
