@@ -106,6 +106,53 @@ __global__ void mnms_prep_kernel(const float *__restrict__ scores, const int32_t
     atomicAdd(cnt + t, 1);
 }
 
+// ---- small tiles (<= 2048 masks each): one counting-sort scatter + one in-shared-memory bitonic sort per tile instead of
+// five device-wide radix passes (a tile holds a few hundred masks; the passes are pure launch latency at that size).
+// Key = (descending score key << 32) | (0xffffffff - index): ascending order = score descending, ties higher index first,
+// the order the stable radix sort of the reversed input produces.
+__global__ void mnms_scatter_kernel(const float *__restrict__ scores, const int32_t *__restrict__ tile, int n, int T,
+                                    const int *__restrict__ seg_start, int *__restrict__ cursor, uint64_t *__restrict__ skey) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int t = tile ? tile[i] : 0;
+    if (t < 0 || t >= T) t = T;
+    const int pos = seg_start[t] + atomicAdd(cursor + t, 1);
+    skey[pos] = ((uint64_t)float_desc_key(scores[i]) << 32) | (uint64_t)(0xffffffffu - (uint32_t)i);
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(256) mnms_blocksort_kernel(const uint64_t *__restrict__ skey, const int *__restrict__ seg_start,
+                                                             int n, int T, int32_t *__restrict__ vals_out) {
+    __shared__ uint64_t s[CAP];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int s0 = seg_start[t];
+    const int cnt = (t < T ? seg_start[t + 1] : n) - s0;
+    if (t == T || cnt > CAP) { // the trash segment needs no order; an over-capacity tile is flagged in status by segments_kernel
+        for (int p = tid; p < cnt; p += 256) vals_out[s0 + p] = (int32_t)(0xffffffffu - (uint32_t)skey[s0 + p]);
+        return;
+    }
+    int P2 = 2;
+    while (P2 < cnt) P2 <<= 1;
+    for (int p = tid; p < P2; p += 256) s[p] = p < cnt ? skey[s0 + p] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = tid; p < P2; p += 256) {
+                const int q = p ^ j;
+                if (q > p) {
+                    const uint64_t a = s[p], b = s[q];
+                    if ((a > b) == ((p & k) == 0)) {
+                        s[p] = b;
+                        s[q] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int p = tid; p < cnt; p += 256) vals_out[s0 + p] = (int32_t)(0xffffffffu - (uint32_t)s[p]);
+}
+
 __global__ void mnms_gather_kernel(const int32_t *__restrict__ area, const int32_t *__restrict__ bbox,
                                    const int32_t *__restrict__ svals, int n, int32_t *__restrict__ sarea,
                                    int4 *__restrict__ sbbox) {
@@ -284,11 +331,19 @@ NUHTC_API int nuhtc_mask_nms(const uint64_t *bits, const int32_t *area, const in
     mnms_init_kernel<<<(T + 256) / 256, 256, 0, st>>>(L.cnt, T + 1, status);
     mnms_prep_kernel<<<nb, 256, 0, st>>>(scores, tile, n, T, L.keys_in, L.vals_in, L.cnt, status);
     segments_kernel<int32_t><<<1, 256, 0, st>>>(L.cnt, T, max_tile_size, L.seg_start, tile_start, status);
-    int tbits = 0;
-    while ((1 << tbits) < T + 1) ++tbits;
-    size_t cub_bytes = L.cub_bytes;
-    NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, n, 0,
-                                               32 + tbits, st));
+    if (max_tile_size <= 2048) {
+        NUHTC_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * (T + 1), st)); // the counts are consumed: reused as scatter cursors
+        mnms_scatter_kernel<<<nb, 256, 0, st>>>(scores, tile, n, T, L.seg_start, L.cnt, L.keys_out);
+        if (max_tile_size <= 512) mnms_blocksort_kernel<512><<<T + 1, 256, 0, st>>>(L.keys_out, L.seg_start, n, T, L.vals_out);
+        else if (max_tile_size <= 1024) mnms_blocksort_kernel<1024><<<T + 1, 256, 0, st>>>(L.keys_out, L.seg_start, n, T, L.vals_out);
+        else mnms_blocksort_kernel<2048><<<T + 1, 256, 0, st>>>(L.keys_out, L.seg_start, n, T, L.vals_out);
+    } else {
+        int tbits = 0;
+        while ((1 << tbits) < T + 1) ++tbits;
+        size_t cub_bytes = L.cub_bytes;
+        NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, n, 0,
+                                                   32 + tbits, st));
+    }
     mnms_gather_kernel<<<nb, 256, 0, st>>>(area, bbox, L.vals_out, n, L.sarea, L.sbbox);
     dim3 mgrid(wpr, wpr, T);
     mnms_mask_kernel<<<mgrid, kMWarps * 32, 0, st>>>(bits, h, wpm, L.vals_out, L.sarea, L.sbbox, L.seg_start, wpr, thr, L.mask);
