@@ -22,6 +22,8 @@
 //             emitted in score order.
 #include <cub/cub.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "greedy_scan.cuh"
 
@@ -128,6 +130,60 @@ __global__ void __launch_bounds__(256) nms_prep_kernel(const float4 *__restrict_
     } else if (live) {
         atomicAdd(cnt + g, 1);
         if (need_max) atomicMax(gmax + g, m);
+    }
+}
+
+// ---- small segments (<= 2048 candidates each): counting-sort scatter + one in-shared-memory bitonic sort per segment
+// instead of five device-wide radix passes.  Key = (descending score key << 32) | index: ascending order = score descending,
+// ties lower index first, exactly the order of the stable radix sort it replaces.
+__global__ void nms_scatter_kernel(const uint64_t *__restrict__ keys_in, int64_t N, const int *__restrict__ seg_start,
+                                   int *__restrict__ cursor, uint64_t *__restrict__ skey) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint64_t k = keys_in[i];
+    const int seg = (int)(k >> 32);
+    const int pos = seg_start[seg] + atomicAdd(cursor + seg, 1);
+    skey[pos] = (k << 32) | (uint64_t)(uint32_t)i;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(256) nms_blocksort_kernel(uint64_t *__restrict__ skey, const int *__restrict__ seg_start, int64_t N,
+                                                            int S, int32_t *__restrict__ vals_out) {
+    __shared__ uint64_t s[CAP];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int s0 = seg_start[t];
+    const int cnt = (t < S ? seg_start[t + 1] : (int)N) - s0;
+    const uint64_t hi = (uint64_t)(uint32_t)t << 32;
+    if (t == S || cnt > CAP) { // the trash segment needs no order; an over-capacity segment is flagged in status
+        for (int p = tid; p < cnt; p += 256) {
+            const uint64_t k = skey[s0 + p];
+            vals_out[s0 + p] = (int32_t)(uint32_t)k;
+            skey[s0 + p] = hi | (k >> 32);
+        }
+        return;
+    }
+    int P2 = 2;
+    while (P2 < cnt) P2 <<= 1;
+    for (int p = tid; p < P2; p += 256) s[p] = p < cnt ? skey[s0 + p] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = tid; p < P2; p += 256) {
+                const int q = p ^ j;
+                if (q > p) {
+                    const uint64_t a = s[p], b = s[q];
+                    if ((a > b) == ((p & k) == 0)) {
+                        s[p] = b;
+                        s[q] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int p = tid; p < cnt; p += 256) {
+        vals_out[s0 + p] = (int32_t)(uint32_t)s[p];
+        skey[s0 + p] = hi | (s[p] >> 32); // back to the (segment, score key) form the later kernels read
     }
 }
 
@@ -376,11 +432,20 @@ NUHTC_API int nuhtc_nms(const float *boxes, const float *scores, const int64_t *
     } else
         nms_prep_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, groups, N, G, offs, L.keys_in, L.vals_in, L.cnt, L.gmax, status);
     segments_kernel<int64_t><<<1, 256, 0, st>>>(L.cnt, S, max_group_size, L.seg_start, Cn > 0 ? L.seg_count : group_start, status);
-    int gbits = 0;
-    while ((1 << gbits) < S + 1) ++gbits;
-    size_t cub_bytes = L.cub_bytes;
-    NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, N, 0,
-                                               32 + gbits, st));
+    static const bool blocksort = getenv("NUHTC_NMS_BLOCKSORT") && getenv("NUHTC_NMS_BLOCKSORT")[0] == '1'; // opt-in until verified on the box
+    if (blocksort && max_group_size <= 2048) {
+        NUHTC_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * (S + 1), st)); // the counts are consumed: reused as scatter cursors
+        nms_scatter_kernel<<<nb, 256, 0, st>>>(L.keys_in, N, L.seg_start, L.cnt, L.keys_out);
+        if (max_group_size <= 512) nms_blocksort_kernel<512><<<S + 1, 256, 0, st>>>(L.keys_out, L.seg_start, N, S, L.vals_out);
+        else if (max_group_size <= 1024) nms_blocksort_kernel<1024><<<S + 1, 256, 0, st>>>(L.keys_out, L.seg_start, N, S, L.vals_out);
+        else nms_blocksort_kernel<2048><<<S + 1, 256, 0, st>>>(L.keys_out, L.seg_start, N, S, L.vals_out);
+    } else {
+        int gbits = 0;
+        while ((1 << gbits) < S + 1) ++gbits;
+        size_t cub_bytes = L.cub_bytes;
+        NUHTC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, N, 0,
+                                                   32 + gbits, st));
+    }
     nms_gather_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, labels, L.keys_out, L.vals_out, L.gmax, N, mode, fo, Cn > 0 ? Cn : 1,
                                           L.sbox, L.sarea, L.slab);
     dim3 mgrid((wpr + kMaskWarps - 1) / kMaskWarps, wpr, S);
