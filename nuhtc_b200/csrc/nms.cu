@@ -432,7 +432,7 @@ NUHTC_API int nuhtc_nms(const float *boxes, const float *scores, const int64_t *
     } else
         nms_prep_kernel<<<nb, 256, 0, st>>>((const float4 *)boxes, scores, groups, N, G, offs, L.keys_in, L.vals_in, L.cnt, L.gmax, status);
     segments_kernel<int64_t><<<1, 256, 0, st>>>(L.cnt, S, max_group_size, L.seg_start, Cn > 0 ? L.seg_count : group_start, status);
-    static const bool blocksort = getenv("NUHTC_NMS_BLOCKSORT") && getenv("NUHTC_NMS_BLOCKSORT")[0] == '1'; // opt-in until verified on the box
+    static const bool blocksort = !(getenv("NUHTC_NMS_BLOCKSORT") && getenv("NUHTC_NMS_BLOCKSORT")[0] == '0'); // A/B switch
     if (blocksort && max_group_size <= 2048) {
         NUHTC_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(int) * (S + 1), st)); // the counts are consumed: reused as scatter cursors
         nms_scatter_kernel<<<nb, 256, 0, st>>>(L.keys_in, N, L.seg_start, L.cnt, L.keys_out);
