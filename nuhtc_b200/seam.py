@@ -199,14 +199,18 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     band_pos = own_pos[bidx]
     halo_pos = inv[N:]
 
-    # ---- resolve: exchange band states, sweep own nuclei, until nobody has an undecided own nucleus
+    # ---- resolve: sweep own nuclei, exchange band states, until nobody has an undecided own nucleus.  ONE collective per
+    # iteration: every rank appends its count of undecided own nuclei (8 bytes) to its band states, so the termination test
+    # rides on the state exchange instead of a separate all-reduce (on 8 GPUs every extra collective is another point where
+    # the slowest host holds everybody up).
+    pcounts = [c + 8 for c in ncounts]
     for _ in range(1 << 20):
-        g_state = _all_gather_ragged(state[band_pos], ncounts, group)
+        remaining = engine.rounds(in_off, indeg, in_list, frozen, state, 8)
+        payload = torch.cat([state[band_pos], remaining.reshape(1).to(torch.int64).view(torch.uint8)])
+        g = _all_gather_ragged(payload, pcounts, group)
+        tot = torch.stack([x[-8:].clone().view(torch.int64) for x in g]).sum()
         if H:
-            state[halo_pos] = torch.cat(g_state)[halo_flat]
-        remaining = engine.rounds(in_off, indeg, in_list, frozen, state, 4)
-        tot = remaining.clone()
-        dist.all_reduce(tot, group=group)
+            state[halo_pos] = torch.cat([x[:-8] for x in g])[halo_flat]
         if int(tot.item()) == 0:
             break
     mark("resolve")
