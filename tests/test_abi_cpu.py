@@ -70,3 +70,26 @@ def test_argument_validation_without_gpu():
     assert L.nuhtc_paste_masks(None, None, 1, 100, 100, 8, 8, 0.5, 1, None, None, None, None) == -1
     assert L.nuhtc_nms_workspace_bytes(5000, 16, 5000, 0) > 5000 * 79 * 8
     assert L.nuhtc_nms_workspace_bytes(0, 1, 0, 0) == 256
+
+
+def test_argument_validation_of_the_later_entry_points():
+    """contours / glue / dual paste: sizes and null pointers are rejected before any CUDA call; empty inputs are accepted"""
+    import ctypes
+    from nuhtc_b200 import _lib
+    L = _lib.lib()
+    F4 = ctypes.c_float * 4
+    one, zero = F4(1, 1, 1, 1), F4(0, 0, 0, 0)
+    assert L.nuhtc_mask_contours(None, None, None, -1, 64, 64, 8, None, None, None, None) == -1
+    assert L.nuhtc_mask_contours(None, None, None, 4, 64, 64, 0, None, None, None, None) == -1        # max_pts < 1
+    assert L.nuhtc_contour_rings(None, None, None, None, 3, 16, None, None) == -1                     # null pointers, n > 0
+    assert L.nuhtc_contour_rings(None, None, None, None, 0, 16, None, None) == 0                      # nothing to do
+    assert L.nuhtc_delta2bbox(None, 1, None, 5, zero, one, 64, 64, 16 / 1000, 1.0, None, None) == -1  # null pointers, K > 0
+    assert L.nuhtc_delta2bbox(None, 1, None, 0, zero, one, 64, 64, 16 / 1000, 1.0, None, None) == 0
+    assert L.nuhtc_delta2bbox(None, 1, None, 0, zero, one, 64, 64, 0.0, 1.0, None, None) == -1        # wh_ratio_clip must be > 0
+    assert L.nuhtc_multiclass_candidates(None, 3, None, 6, None, 5, 4, 5, 0.05, None, None, None, None, None, None) == -1  # stride < 4
+    assert L.nuhtc_detection_slots(None, None, None, 0, 10, None, None, None, None, 1.0, None, None, None, None, None, None, None, None) == -1
+    assert L.nuhtc_tile_filter(None, None, None, 0, 0, 256, 256, 10, None, None) == 0
+    assert L.nuhtc_keep_flags(None, None, None, 0, 10, 5, None, None) == -1                           # num_tiles < 1
+    assert L.nuhtc_paste_masks_dense_bits(None, None, 2, 28, 28, 64, 60, 0.5, None, None, None, None, None) == -1   # width % 16
+    assert b"multiple of 16" in L.nuhtc_last_error()
+    assert L.nuhtc_paste_masks_dense_bits(None, None, 0, 28, 28, 64, 64, 0.5, None, None, None, None, None) == 0
