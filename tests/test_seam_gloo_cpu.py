@@ -87,7 +87,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,tiles", [(2, (3, 4)), (3, (2, 5))])
+@pytest.mark.parametrize("world,tiles", [(2, (3, 4)), (3, (2, 5)), (4, (2, 3))])   # the last one leaves rank 3 without tiles
 def test_distributed_merge_equals_single_process(oracle, world, tiles):
     from nuhtc_b200 import synth
     slide = synth.slide_nuclei(tiles[0], tiles[1], per_tile=6, seed=4)
