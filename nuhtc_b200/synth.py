@@ -18,12 +18,22 @@ def fpn_levels(B: int, C: int, frame: int = 512, seed: int = 0, device="cpu") ->
 
 def proposals(B: int, n_per: int, dist: str = "nuclei", frame: int = 512, seed: int = 0) -> torch.Tensor:
     """rois [B*n_per, 5] in the network frame.  'nuclei': side U(16,64) px (all route to level 0);
-    'routed': side log-U(16,512) px (all four levels)."""
+    'routed': side log-U(16,512) px (all four levels); 'clustered': like 'nuclei', but the proposals of a tile sit on ~150
+    nucleus centres with a few px of jitter, the way RPN proposals that survived NMS(0.7) crowd around objects (analysis
+    distribution for window sharing, see tools/window_sharing.py; not a bench default)."""
     g = torch.Generator().manual_seed(seed + 17)
     K = B * n_per
     ctr = torch.rand(K, 2, generator=g) * frame
     if dist == "nuclei":
         wh = 16 + torch.rand(K, 2, generator=g) * 48
+    elif dist == "clustered":
+        nn = 150
+        cen = torch.rand(B, nn, 2, generator=g) * frame
+        size = 16 + torch.rand(B, nn, 2, generator=g) * 48
+        pick = torch.randint(0, nn, (B, n_per), generator=g)
+        bi = torch.arange(B)[:, None].expand(B, n_per)
+        ctr = (cen[bi, pick] + torch.randn(B, n_per, 2, generator=g) * 2.0).reshape(K, 2)
+        wh = (size[bi, pick] * (0.9 + 0.2 * torch.rand(B, n_per, 2, generator=g))).reshape(K, 2)
     elif dist == "routed":
         side = torch.exp(torch.rand(K, 1, generator=g) * (math.log(512) - math.log(16)) + math.log(16))
         wh = side * (0.75 + 0.5 * torch.rand(K, 2, generator=g))
