@@ -1,4 +1,6 @@
 """CPU: host-side logic of the package (no CUDA calls)."""
+import os
+
 import numpy as np
 import torch
 
@@ -66,3 +68,23 @@ def test_tile_features_wire_format_and_sidecar(tmp_path):
     xy3, voff3, sc3, lab3, bb3 = read_sidecar(path)
     assert np.array_equal(xy3, ring_xy) and np.array_equal(voff3, voff) and np.array_equal(lab3, labels)
     assert np.allclose(sc3, scores) and np.allclose(bb3, boxes)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs first) prints ONE JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-tiles", "1", "--proposals", "60"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "wsi_tiles_per_sec_roi_stage_plus_merge" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
