@@ -29,15 +29,22 @@ void nuhtc_set_error(const char *fmt, ...);
 
 #define NUHTC_LAUNCH_CHECK() NUHTC_CUDA(cudaGetLastError())
 
+// Function attributes (opt-in shared memory), occupancy-derived grid sizes and the SM count belong to a DEVICE, not to
+// the process: every cache of them is an array indexed by the current device ordinal, so one process may drive several GPUs.
+constexpr int kNuhtcMaxDevices = 64;
+static inline int nuhtc_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= kNuhtcMaxDevices) ? 0 : dev;
+}
 static inline int nuhtc_sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kNuhtcMaxDevices] = {0};
+    const int dev = nuhtc_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(kScanThreads) greedy_scan_kernel(const uint64_
 template <typename OutT>
 static int launch_greedy_scan(const uint64_t *mask, const int32_t *svals, const int *seg_start, int wpr, int G, OutT *keep,
                               OutT *group_count, cudaStream_t st, const uint64_t *skeys = nullptr, uint64_t *kkeys = nullptr) {
-    static bool attr_done = false;
+    static bool attr_done_dev[kNuhtcMaxDevices] = {false};
+    bool &attr_done = attr_done_dev[nuhtc_device()];   // the attribute is per device
     if ((size_t)wpr * 8 > 200 * 1024) {
         nuhtc_set_error("greedy scan: segment too large for the shared removed-set");
         return NUHTC_EINVAL;

@@ -31,17 +31,18 @@ struct RoiLevels {
     int L;
 };
 
-// SingleRoIExtractor.map_roi_levels: floor(log2(sqrt(w*h)/finest + 1e-6)) clamped to [0, L-1].
-// floor(log2 v) >= k  <=>  v >= 2^k, so the level is found by comparisons (no log2 rounding).
+// SingleRoIExtractor.map_roi_levels (single_level_roi_extractor.py:51-55):
+//   torch.floor(torch.log2(sqrt(w*h)/finest + 1e-6)).clamp(0, L-1)
+// The reference evaluates log2 in fp32, so a value just below a power of two can round UP to the integer and land one
+// level higher than the exact logarithm would put it.  The same fp32 chain is evaluated here: IEEE sub/mul/sqrt/div/add
+// and libdevice log2f, the function ATen's CUDA log2 kernel calls (tests/test_gpu_roi_align.py sweeps every float
+// around the level boundaries against torch.floor(torch.log2(.)) on the device).
 __device__ __forceinline__ int route_level(const float *roi, int L, float finest) {
     const float s = __fsqrt_rn(__fmul_rn(__fsub_rn(roi[3], roi[1]), __fsub_rn(roi[4], roi[2])));
     const float v = __fadd_rn(__fdiv_rn(s, finest), 1e-6f);
+    const float f = floorf(log2f(v));   // NaN (negative area) and -inf (v == 0 cannot happen: + 1e-6) clamp to level 0
     int l = 0;
-    float p2 = 2.0f;
-    for (int k = 1; k < L; ++k) {
-        if (v >= p2) l = k;
-        p2 *= 2.0f;
-    }
+    if (f >= 1.0f) l = f >= (float)(L - 1) ? L - 1 : (int)f;
     return l;
 }
 
@@ -463,11 +464,12 @@ static size_t sep_smem_bytes() {
 template <int P, int NQ, int PHS, int VEC, int MINB>
 static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
                       float *out, const float *bias, cudaStream_t st) {
-    static bool attr_done = false;
+    static bool attr_done[kNuhtcMaxDevices] = {false};
+    const int dev = nuhtc_device();
     const size_t smem = sep_smem_bytes<P, NQ, VEC>();
-    if (!attr_done) {
+    if (!attr_done[dev]) {
         NUHTC_CUDA(cudaFuncSetAttribute(roi_align_sep_kernel<P, NQ, PHS, VEC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     dim3 grid(K, C / (NQ * 4 * VEC));
     roi_align_sep_kernel<P, NQ, PHS, VEC, MINB><<<grid, NQ * P * PHS, smem, st>>>(lv, C, rois, sr, aligned, mode, finest, out, bias);
@@ -977,7 +979,8 @@ static bool build_tmaps(const RoiLevels &lv, int B, int C, int CC, RoiTmaps *tm)
 template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
 static int launch_pipe(const RoiLevels &lv, int B, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
                        float *out, const float *bias, cudaStream_t st) {
-    static int grid_cached = 0;
+    static int grid_cache[kNuhtcMaxDevices] = {0};
+    int &grid_cached = grid_cache[nuhtc_device()];
     static_assert(WMAX <= tmap_box_px(kTmapBoxes - 1) || true, "");
     RoiTmaps tm;
     memset(&tm, 0, sizeof tm);

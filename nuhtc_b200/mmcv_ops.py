@@ -241,8 +241,22 @@ def _nms_single(boxes, scores, labels, iou_threshold, offset, mode) -> torch.Ten
         top = int(labels.max().item()) + 1
         if int(labels.min().item()) >= 0 and top <= 4096:
             ncls = top
+    elif mode == "offset" and labels is not None:
+        # below split_thr mmcv runs ONE nms over the offset boxes.  Class segments give the identical result as long as no
+        # coordinate is negative (then boxes of different classes cannot overlap after the offset) and do 1/num_classes
+        # of the pair tests; the kernel verifies the precondition itself (status 3) and the call is repeated without
+        # segments when it does not hold.
+        top = int(labels.max().item()) + 1
+        if int(labels.min().item()) >= 0 and top <= 4096:
+            ncls = top
     keep, _, gcount, status = nms_groups(boxes, scores, labels, None, 1, N, iou_threshold, offset, mode, num_classes=ncls)
-    k = int(gcount.item())  # the op returns a data-dependent shape, as mmcv's does
+    k, st = (int(v) for v in torch.stack([gcount[0], status[0].to(gcount.dtype)]).tolist())  # one D2H: mmcv's op syncs too
+    if st == 3 and ncls > 0:   # a negative coordinate: the all-pairs test on the offset boxes is the contract
+        keep, _, gcount, status = nms_groups(boxes, scores, labels, None, 1, N, iou_threshold, offset, mode, num_classes=0)
+        k, st = (int(v) for v in torch.stack([gcount[0], status[0].to(gcount.dtype)]).tolist())
+    if st != 0:
+        raise L.NuhtcError(f"nms: device status {st} (1: a sort segment exceeded its capacity, 2: a label outside "
+                           f"[0, num_classes), 3: negative coordinate with class segments)")
     return keep[:k]
 
 

@@ -94,12 +94,16 @@ class RoIStageResult:
             return self
         v = self.det_valid
         new_index = torch.cumsum(v.to(torch.int64), 0) - 1
-        nk = int(self.tile_count.sum().item())
-        keep = self.keep.clone()
-        keep[:nk] = new_index[self.keep[:nk].long()].to(self.keep.dtype)
+        # tile t's kept list sits at keep[tile_start[t] : tile_start[t]+tile_count[t]] and tile_start is the scan of the
+        # ENTRANT counts, so the lists are not packed from 0: gather them tile by tile into a packed list
+        ts, tc = self.tile_start.cpu().tolist(), self.tile_count.cpu().tolist()
+        parts = [new_index[self.keep[s:s + c].long()].to(self.keep.dtype) for s, c in zip(ts, tc)]
+        keep = torch.cat(parts) if parts else self.keep[:0]
+        tcount = self.tile_count.clone()
+        tstart = (torch.cumsum(tcount, 0) - tcount).to(self.tile_start.dtype)
         return RoIStageResult(self.det_boxes[v], self.det_scores[v], self.det_labels[v], self.det_tile[v],
                               None if self.masks is None else self.masks[v], self.mask_bits[v], self.mask_area[v], keep,
-                              self.tile_start, self.tile_count, det_valid=None, det_cand=self.det_cand[v], status=None,
+                              tstart, tcount, det_valid=None, det_cand=self.det_cand[v], status=None,
                               contour_xy=None if self.contour_xy is None else self.contour_xy[v],
                               contour_count=None if self.contour_count is None else self.contour_count[v])
 

@@ -60,6 +60,10 @@ def lib():
         L.oracle_poly_iou.restype = ctypes.c_double
         L.oracle_merge.argtypes = [c_dp, c_i64p, c_dp, ctypes.c_int64, ctypes.c_double, ctypes.c_int, c_i64p]
         L.oracle_merge.restype = ctypes.c_int64
+        L.oracle_merge_check.argtypes = [c_dp, c_i64p, c_dp, ctypes.c_int64, ctypes.c_double, ctypes.c_int, c_i64p, ctypes.c_int, c_dp, ctypes.c_double, c_i64p, ctypes.c_int64, c_i64p]
+        L.oracle_merge_check.restype = ctypes.c_int64
+        L.oracle_poly_inter_area_slab.argtypes = [c_dp, ctypes.c_int, c_dp, ctypes.c_int]
+        L.oracle_poly_inter_area_slab.restype = ctypes.c_double
         L.oracle_paste.argtypes = [c_fp, c_fp] + [ctypes.c_int] * 5 + [c_fp, ctypes.c_int]
         L.oracle_contour0.argtypes = [c_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int]
         _lib = L
@@ -398,6 +402,13 @@ def poly_inter_area(P: np.ndarray, Q: np.ndarray) -> float:
     return lib().oracle_poly_inter_area(_dp(p), p.shape[0], _dp(q), q.shape[0])
 
 
+def poly_inter_area_slab(P: np.ndarray, Q: np.ndarray) -> float:
+    """Independent second algorithm (vertical slabs + even-odd rule) -- anchors poly_inter_area in the tests."""
+    p = np.ascontiguousarray(P, dtype=np.float64)
+    q = np.ascontiguousarray(Q, dtype=np.float64)
+    return lib().oracle_poly_inter_area_slab(_dp(p), p.shape[0], _dp(q), q.shape[0])
+
+
 def poly_iou(P: np.ndarray, Q: np.ndarray) -> float:
     p = np.ascontiguousarray(P, dtype=np.float64)
     q = np.ascontiguousarray(Q, dtype=np.float64)
@@ -416,3 +427,67 @@ def merge_overlap_arrays(xy: np.ndarray, voff: np.ndarray, score: np.ndarray, ov
     strat = {"probability": 0, "area": 1}[merge_strategy]
     k = lib().oracle_merge(_dp(xy), _i64p(voff), _dp(score), N, float(overlap_threshold), strat, _i64p(out))
     return out[:k]
+
+
+def merge_overlap_arrays_check(xy, voff, score, overlap_threshold=0.01, merge_strategy="probability", naive=True,
+                               slab=False, with_margin=False):
+    """Same greedy loop with an O(N^2) candidate search (naive) and / or the slab-decomposition area (slab): the
+    independent cross-checks of merge_overlap_arrays."""
+    xy = np.ascontiguousarray(xy, dtype=np.float64)
+    voff = np.ascontiguousarray(voff, dtype=np.int64)
+    score = np.ascontiguousarray(score, dtype=np.float64)
+    N = score.shape[0]
+    out = np.empty(N, dtype=np.int64)
+    strat = {"probability": 0, "area": 1}[merge_strategy]
+    margin = ctypes.c_double(0.0)
+    ties = np.zeros((4096, 2), dtype=np.int64)
+    nties = ctypes.c_int64(0)
+    k = lib().oracle_merge_check(_dp(xy), _i64p(voff), _dp(score), N, float(overlap_threshold), strat, _i64p(out),
+                                 int(bool(naive)) | (int(bool(slab)) << 1), ctypes.byref(margin), 1e-9, _i64p(ties),
+                                 ties.shape[0], ctypes.byref(nties))
+    if with_margin:   # min |IoU - thr| over the decisive pairs + the pairs below 1e-9 (outside the parity contract)
+        return out[:k], margin.value, ties[: nties.value].copy()
+    return out[:k]
+
+
+def drop_threshold_ties(d: dict, overlap_threshold: float, max_rounds: int = 8):
+    """Integer-vertex polygons make IoU a rational that CAN equal the threshold exactly (e.g. 74/3 / 1480/3 = 1/20), and
+    what GEOS's double arithmetic decides there is a coin flip: |IoU - thr| < 1e-9 is outside the parity contract
+    (SURVEY.md H3).  Golden cases therefore drop the lower-scored nucleus of every such decisive pair -- and the lower-scored
+    copies of identical rings (see below).  Returns (cleaned dict, sorted removed original indices)."""
+    xy, voff, score = d["xy"], d["voff"], d["score"]
+    alive = np.ones(len(score), dtype=bool)
+    # identical rings: the reference keys a dict by the shapely polygon (nuclei_merge.py:101-103), so geometrically
+    # identical nuclei collide and it keeps the LOWER-scored copy -- out of contract like score ties; keep the top copy only
+    best = {}
+    for i in range(len(score)):
+        key = xy[voff[i]:voff[i + 1]].tobytes()
+        j = best.get(key)
+        if j is None:
+            best[key] = i
+        else:
+            lo, hi = (i, j) if score[i] < score[j] else (j, i)
+            alive[lo] = False
+            best[key] = hi
+    for _ in range(max_rounds):
+        idx = np.nonzero(alive)[0]
+        cnt = np.diff(voff)[idx]
+        nv = np.zeros(len(idx) + 1, dtype=np.int64)
+        nv[1:] = np.cumsum(cnt)
+        sel = np.repeat(voff[:-1][idx], cnt) + (np.arange(nv[-1]) - np.repeat(nv[:-1], cnt))
+        sub = dict(xy=xy[sel], voff=nv, score=score[idx])
+        ties = set()
+        for strat in ("probability", "area"):
+            _, _, t = merge_overlap_arrays_check(sub["xy"], sub["voff"], sub["score"], overlap_threshold, strat, naive=False,
+                                                 with_margin=True)
+            ties |= {(int(a), int(b)) for a, b in t}
+        if not ties:
+            out = dict(d)
+            out.update(sub)
+            if "tile_id" in d:
+                out["tile_id"] = d["tile_id"][idx]
+            return out, np.nonzero(~alive)[0]
+        for a, b in ties:
+            lo = a if sub["score"][a] < sub["score"][b] else b
+            alive[idx[lo]] = False
+    raise RuntimeError("threshold ties remain")

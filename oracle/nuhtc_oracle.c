@@ -394,6 +394,88 @@ API double oracle_poly_iou(const double *P, int n, const double *Q, int m) {
     return inter / (aP + aQ - inter);
 }
 
+/* ------------------------------------------------------------------------ */
+/* SECOND, INDEPENDENT anchor for the polygon intersection area: a vertical    */
+/* slab decomposition with the even-odd rule.  It shares nothing with          */
+/* oracle_poly_inter_area above (no orientation, no signed trapezoids, no      */
+/* butterfly summation): the x axis is cut at every vertex and every proper    */
+/* edge crossing; inside a slab no two edges cross, so each polygon is a        */
+/* sorted stack of y-intervals (consecutive pairs of its edges that span the   */
+/* slab) bounded by lines, and the area of the overlap of two such intervals    */
+/* is (width) x (overlap height at mid-slab), exact for linear bounds.         */
+/* Used only by tests/test_oracle_cpu.py to check the trapezoid oracle on      */
+/* >= 1e4 contour-shaped pairs ("bent to the kernel").             */
+/* ------------------------------------------------------------------------ */
+static int dbl_asc(const void *a, const void *b) {
+    const double x = *(const double *)a, y = *(const double *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+typedef struct { double ym, y0, y1; } slab_edge_t;
+static int slab_edge_asc(const void *a, const void *b) {
+    const slab_edge_t *x = (const slab_edge_t *)a, *y = (const slab_edge_t *)b;
+    if (x->ym < y->ym) return -1;
+    if (x->ym > y->ym) return 1;
+    /* equal at mid-slab (two edges that meet only at a slab boundary cannot be; collinear ones can): any order */
+    return 0;
+}
+static int slab_collect(const double *P, int n, double xa, double xb, slab_edge_t *out) {
+    int k = 0;
+    const double xm = 0.5 * (xa + xb);
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        double x0 = P[2 * i], y0 = P[2 * i + 1], x1 = P[2 * j], y1 = P[2 * j + 1];
+        if (x0 == x1) continue;
+        if (x0 > x1) { double t; t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+        if (x0 <= xa && x1 >= xb) {
+            const double m = (y1 - y0) / (x1 - x0);
+            out[k].ym = y0 + m * (xm - x0);
+            out[k].y0 = y0 + m * (xa - x0);
+            out[k].y1 = y0 + m * (xb - x0);
+            ++k;
+        }
+    }
+    qsort(out, k, sizeof(slab_edge_t), slab_edge_asc);
+    return k;
+}
+API double oracle_poly_inter_area_slab(const double *P, int n, const double *Q, int m) {
+    if (n < 3 || m < 3) return 0.0;
+    int cap = n + m + n * m, nx = 0;
+    double *xs = (double *)malloc(sizeof(double) * cap);
+    for (int i = 0; i < n; ++i) xs[nx++] = P[2 * i];
+    for (int j = 0; j < m; ++j) xs[nx++] = Q[2 * j];
+    for (int i = 0; i < n; ++i) {
+        const int i1 = (i + 1 == n) ? 0 : i + 1;
+        const double ax = P[2 * i], ay = P[2 * i + 1], bx = P[2 * i1], by = P[2 * i1 + 1];
+        for (int j = 0; j < m; ++j) {
+            const int j1 = (j + 1 == m) ? 0 : j + 1;
+            const double cx = Q[2 * j], cy = Q[2 * j + 1], dx = Q[2 * j1], dy = Q[2 * j1 + 1];
+            const double den = (bx - ax) * (dy - cy) - (by - ay) * (dx - cx);
+            if (den == 0.0) continue; /* parallel or collinear: no isolated crossing */
+            const double t = ((cx - ax) * (dy - cy) - (cy - ay) * (dx - cx)) / den;
+            const double u = ((cx - ax) * (by - ay) - (cy - ay) * (bx - ax)) / den;
+            if (t > 0.0 && t < 1.0 && u > 0.0 && u < 1.0) xs[nx++] = ax + t * (bx - ax);
+        }
+    }
+    qsort(xs, nx, sizeof(double), dbl_asc);
+    slab_edge_t *ep = (slab_edge_t *)malloc(sizeof(slab_edge_t) * n), *eq = (slab_edge_t *)malloc(sizeof(slab_edge_t) * m);
+    double area = 0.0;
+    for (int s = 0; s + 1 < nx; ++s) {
+        const double xa = xs[s], xb = xs[s + 1];
+        if (!(xb > xa)) continue;
+        const int kp = slab_collect(P, n, xa, xb, ep), kq = slab_collect(Q, m, xa, xb, eq);
+        for (int a = 0; a + 1 < kp; a += 2)
+            for (int b = 0; b + 1 < kq; b += 2) {
+                /* interval a of P = [ep[a], ep[a+1]], interval b of Q likewise; their bounds are lines that do not
+                   cross inside the slab, so max/min of the bounds is decided at mid-slab */
+                const double lo = ep[a].ym > eq[b].ym ? ep[a].ym : eq[b].ym;
+                const double hi = ep[a + 1].ym < eq[b + 1].ym ? ep[a + 1].ym : eq[b + 1].ym;
+                if (hi > lo) area += (hi - lo) * (xb - xa);
+            }
+    }
+    free(xs); free(ep); free(eq);
+    return area;
+}
+
 /* Greedy cross-tile merge (tools/nuclei_merge.py:62-174).
  *   xy      : concatenated rings, doubles [sum V, 2]
  *   voff    : [N+1] ring offsets into xy (in vertices)
@@ -414,8 +496,12 @@ static int i64_asc(const void *a, const void *b) {
     return x < y ? -1 : (x > y ? 1 : 0);
 }
 
-API int64_t oracle_merge(const double *xy, const int64_t *voff, const double *score, int64_t N,
-                         double thr, int strategy, int64_t *out_ids) {
+/* optional probe of the decisive pairs (the pairs the greedy loop evaluates): min |IoU - thr| and the pairs closer to
+ * the threshold than eps (original indices, query first) */
+typedef struct { double eps; int64_t cap, n; int64_t *pairs; double min_margin; } merge_probe_t;
+static int64_t merge_impl(const double *xy, const int64_t *voff, const double *score, int64_t N,
+                          double thr, int strategy, int64_t *out_ids, int naive, int slab, merge_probe_t *probe) {
+    if (probe) { probe->min_margin = 1e300; probe->n = 0; }
     if (N <= 0) return 0;
     dsc_t *ord = (dsc_t *)malloc(N * sizeof(dsc_t));
     for (int64_t i = 0; i < N; ++i) { ord[i].s = score[i]; ord[i].i = i; }
@@ -471,25 +557,35 @@ API int64_t oracle_merge(const double *xy, const int64_t *voff, const double *sc
         const int qV = (int)(voff[qi + 1] - voff[qi]);
         const int64_t cx = cellof[r] % nx, cy = cellof[r] / nx;
         int64_t best = -1; double best_area = -1.0;
+#define MERGE_TRY(s_) do { const int64_t s = (s_);                                                                        \
+            if (s == r || iter[s]) break;                                                                               \
+            if (bx0[s] > bx1[r] || bx1[s] < bx0[r] || by0[s] > by1[r] || by1[s] < by0[r]) break;                        \
+            const int64_t si = ord[s].i;                                                                                \
+            const double inter = slab ? oracle_poly_inter_area_slab(qp, qV, xy + 2 * voff[si], (int)(voff[si + 1] - voff[si])) \
+                                      : oracle_poly_inter_area(qp, qV, xy + 2 * voff[si], (int)(voff[si + 1] - voff[si]));    \
+            const double iou = inter / (ar[r] + ar[s] - inter);                                                         \
+            if (probe) {                                                                                                \
+                const double mg = fabs(iou - thr);                                                                      \
+                if (mg < probe->min_margin) probe->min_margin = mg;                                                     \
+                if (mg < probe->eps && probe->n < probe->cap) {                                                         \
+                    probe->pairs[2 * probe->n] = ord[r].i; probe->pairs[2 * probe->n + 1] = si; probe->n++; }           \
+            }                                                                                                           \
+            if (iou > thr) {                                                                                            \
+                iter[s] = 1;                                                                                            \
+                if (ar[s] > best_area || (ar[s] == best_area && s < best)) { best_area = ar[s]; best = s; }             \
+            } } while (0)
+        if (naive) { /* every polygon whose envelope intersects the query's: what STRtree.query returns, found the O(N) way */
+            for (int64_t s2 = 0; s2 < N; ++s2) MERGE_TRY(s2);
+        } else
         for (int64_t yy = cy - 1; yy <= cy + 1; ++yy) {
             if (yy < 0 || yy >= ny) continue;
             for (int64_t xx = cx - 1; xx <= cx + 1; ++xx) {
                 if (xx < 0 || xx >= nx) continue;
                 const int64_t c = yy * nx + xx;
-                for (int64_t q = cstart[c]; q < cstart[c + 1]; ++q) {
-                    const int64_t s = items[q];
-                    if (s == r || iter[s]) continue;
-                    if (bx0[s] > bx1[r] || bx1[s] < bx0[r] || by0[s] > by1[r] || by1[s] < by0[r]) continue;
-                    const int64_t si = ord[s].i;
-                    const double inter = oracle_poly_inter_area(qp, qV, xy + 2 * voff[si], (int)(voff[si + 1] - voff[si]));
-                    const double iou = inter / (ar[r] + ar[s] - inter);
-                    if (iou > thr) {
-                        iter[s] = 1;
-                        if (ar[s] > best_area || (ar[s] == best_area && s < best)) { best_area = ar[s]; best = s; }
-                    }
-                }
+                for (int64_t q = cstart[c]; q < cstart[c + 1]; ++q) MERGE_TRY(items[q]);
             }
         }
+#undef MERGE_TRY
         kept_rank[k++] = (strategy == 1 && best >= 0) ? best : r;
         iter[r] = 1;
     }
@@ -498,6 +594,23 @@ API int64_t oracle_merge(const double *xy, const int64_t *voff, const double *sc
     for (int64_t q = 0; q < k; ++q) out_ids[q] = ord[kept_rank[q]].i;
     free(ord); free(bx0); free(by0); free(bx1); free(by1); free(ar); free(cstart); free(cellof);
     free(fill); free(items); free(iter); free(kept_rank);
+    return k;
+}
+API int64_t oracle_merge(const double *xy, const int64_t *voff, const double *score, int64_t N,
+                         double thr, int strategy, int64_t *out_ids) {
+    return merge_impl(xy, voff, score, N, thr, strategy, out_ids, 0, 0, NULL);
+}
+/* flags bit 0: O(N^2) candidate search (every envelope pair) instead of the grid; bit 1: slab-decomposition area.
+ * min_margin (may be NULL): min |IoU - thr| over the pairs the greedy loop evaluated, i.e. the pairs whose decision
+ * shapes the result -- pairs closer than 1e-9 to the threshold are outside the parity contract (an integer-vertex IoU
+ * can equal 1/20 exactly).  Cross-checks of the fast oracle, used by tests/ only. */
+API int64_t oracle_merge_check(const double *xy, const int64_t *voff, const double *score, int64_t N,
+                               double thr, int strategy, int64_t *out_ids, int flags, double *min_margin,
+                               double eps, int64_t *tie_pairs, int64_t tie_cap, int64_t *num_ties) {
+    merge_probe_t pr = {eps, tie_pairs ? tie_cap : 0, 0, tie_pairs, 1e300};
+    const int64_t k = merge_impl(xy, voff, score, N, thr, strategy, out_ids, flags & 1, (flags >> 1) & 1, &pr);
+    if (min_margin) *min_margin = pr.min_margin;
+    if (num_ties) *num_ties = pr.n;
     return k;
 }
 

@@ -24,6 +24,21 @@ def test_merge_exact(oracle, tiles, strategy):
     assert got.dtype == np.int64 and len(got) == len(ref) and (got == ref).all()
 
 
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_merge_exact_at_cfg5_sizes(oracle, case):
+    """BASELINE cfg 5: ~15k / ~170k / ~1.7M nuclei (208 x 208 tiles).  The CUDA merge must reproduce the oracle's kept ids
+    (values and order) -- compared directly (the grid oracle needs ~7 s at 1.7M) and against the committed golden hashes
+    (tests/golden/merge_large.json, made by tests/golden/make_merge_golden.py; exact-threshold pairs dropped there)."""
+    from _slides import load_case, sha
+    c, d, thr = load_case(case)
+    for strat in ("probability", "area"):
+        got = _run(d, thr, strat)
+        assert len(got) == c[strat]["kept"]
+        assert sha(got.astype(np.int64)) == c[strat]["kept_ids_sha256"], strat
+        if strat == "probability" or case < 2:
+            assert np.array_equal(got, oracle.merge_overlap_arrays(d["xy"], d["voff"], d["score"], thr, strat))
+
+
 def test_merge_thresholds_and_degenerate(oracle):
     from nuhtc_b200 import synth
     d = synth.slide_nuclei(5, 5, per_tile=30, seed=9)

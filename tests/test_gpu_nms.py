@@ -98,6 +98,47 @@ def test_grouped_nms_equals_per_image_calls(oracle):
         assert torch.equal(got, idx[k_ref]), g
 
 
+@pytest.mark.parametrize("N", [50000, 100000, 200000])
+def test_batched_nms_large_sweep_exact(oracle, N):
+    """BASELINE cfg 3 (large half): keep lists identical (values and order) to the oracle at 50k / 100k / 200k boxes
+    (mmcv's per-class loop above split_thr, /root/reference/nuhtc/models/bbox_head.py:93); the oracle needs ~1-16 s."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    boxes, scores, labels = synth.nms_boxes(N, seed=3)
+    cfg = dict(type="nms", iou_threshold=0.5)
+    d_ref, k_ref = oracle.batched_nms(boxes, scores, labels, cfg)
+    d, k = nb.batched_nms(boxes.cuda(), scores.cuda(), labels.cuda(), cfg)
+    assert 0.2 < len(k_ref) / N < 0.8
+    assert torch.equal(k.cpu(), k_ref)
+    assert torch.equal(d.cpu(), d_ref)
+    if N > 50000:
+        return
+    # score_thr 0.05 of the sweep (multiclass_nms filters before batched_nms, bbox_head.py:60-74)
+    m = scores > 0.05
+    idx = m.nonzero().squeeze(1)
+    _, k_ref2 = oracle.batched_nms(boxes[idx], scores[idx], labels[idx], cfg)
+    _, k2 = nb.batched_nms(boxes[idx].cuda(), scores[idx].cuda(), labels[idx].cuda(), cfg)
+    assert torch.equal(k2.cpu(), k_ref2)
+
+
+def test_batched_nms_negative_coordinates_fall_back_to_all_pairs(oracle):
+    """Below split_thr mmcv runs one nms over the offset boxes; with a negative coordinate boxes of different classes CAN
+    overlap after the offset, so the class-segmented fast path must hand over to the all-pairs form (device status 3)."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    boxes, scores, labels = synth.nms_boxes(6000, seed=21, density=30.0)
+    boxes = boxes - boxes.max() * 0.75          # most coordinates negative: offsets no longer separate the classes
+    cfg = dict(type="nms", iou_threshold=0.5)
+    _, k_ref = oracle.batched_nms(boxes, scores, labels, cfg)
+    _, k = nb.batched_nms(boxes.cuda(), scores.cuda(), labels.cuda(), cfg)
+    assert torch.equal(k.cpu(), k_ref)
+    # and the segmented path itself (non-negative coordinates) against the same oracle
+    boxes2 = boxes - boxes.min() + 1.0
+    _, k_ref2 = oracle.batched_nms(boxes2, scores, labels, cfg)
+    _, k2 = nb.batched_nms(boxes2.cuda(), scores.cuda(), labels.cuda(), cfg)
+    assert torch.equal(k2.cpu(), k_ref2)
+
+
 @pytest.mark.parametrize("N", [50000, 200000])
 def test_large_sweep_properties(N):
     """BASELINE cfg 3 (large half) through size-independent properties: the kept set is conflict-free, every dropped

@@ -98,6 +98,86 @@ def test_level_sum_matches_attention_extractor_roialign_branch(oracle, P, sr):
     assert (out - ref).abs().max().item() <= 2 * TOL  # two pooled terms are added
 
 
+def _kernel_levels(rois, impl="auto", C=64, frame=512):
+    """The level the KERNEL routes every RoI to: level l is a constant map of value l+1, so any bin of the routed output
+    reads it back (the RoIs are kept inside the frame so that every sample lands in the map)."""
+    import nuhtc_b200 as nb
+    feats = [torch.full((1, C, frame // s, frame // s), float(l + 1), device="cuda") for l, s in enumerate((4, 8, 16, 32))]
+    out = nb.roi_align_levels(feats, rois.cuda(), 7, [1 / 4, 1 / 8, 1 / 16, 1 / 32], 2, mode="route", finest_scale=56, impl=impl)
+    lv = out[:, 0, 3, 3].round().long() - 1
+    assert torch.equal(out, (lv + 1).float()[:, None, None, None].expand_as(out))
+    return lv.cpu()
+
+
+@pytest.mark.parametrize("impl", ["auto", "direct"])
+def test_routing_matches_golden_levels(impl):
+    """tests/golden/roi_levels.npz: levels produced by executing the reference's own map_roi_levels source
+    (single_level_roi_extractor.py:36-55, make_golden.py) -- here against the routing INSIDE the CUDA kernels."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "roi_levels.npz"))
+    rois = torch.from_numpy(z["rois"]).clone()      # boundary boxes (0,0,112,112), (0,0,111.99,112), ... + random ones
+    assert float(rois[:, 1:].min()) >= 0 and float(rois[:, 1:].max()) <= 512
+    rois[:, 0] = 0
+    got = _kernel_levels(rois, impl, frame=512)
+    assert torch.equal(got, torch.from_numpy(z["levels"]))
+    assert set(got.tolist()) == {0, 1, 2, 3}
+
+
+@pytest.mark.parametrize("impl", ["auto", "direct"])
+def test_routing_at_level_boundaries_every_float(impl):
+    """map_roi_levels is floor(log2(v)) evaluated in fp32, so just below a power of two the logarithm can round up to the
+    integer.  Sweep +-3000 consecutive floats of the box side around each boundary (v = 2, 4, 8) and compare the kernel's
+    level with the reference expression evaluated by torch on the same device."""
+    rows = []
+    for k in (1, 2, 3):
+        side0 = torch.tensor(56.0 * (2.0 ** k - 1e-6), dtype=torch.float32)
+        bits = side0.view(torch.int32) + torch.arange(-3000, 3001, dtype=torch.int32)
+        side = bits.view(torch.float32)
+        x1 = torch.zeros_like(side)      # x2 - x1 == side exactly
+        rows.append(torch.stack([torch.zeros_like(side), x1, x1, x1 + side, x1 + side], 1))
+        # rectangles: sqrt(w*h) falls between representable sides
+        rows.append(torch.stack([torch.zeros_like(side), x1, x1, x1 + side, x1 + side0.expand_as(side).clone()], 1))
+    rois = torch.cat(rows).contiguous()
+    r = rois.cuda()
+    scale = torch.sqrt((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]))
+    v = scale / 56 + 1e-6
+    ref = torch.floor(torch.log2(v)).clamp(min=0, max=3).long().cpu()     # single_level_roi_extractor.py:51-55 on the device
+    got = _kernel_levels(rois, impl)
+    assert torch.equal(got, ref)
+    # the sweep really crosses each boundary, and holds values whose fp32 log2 rounds up across it
+    assert set(ref.tolist()) == {0, 1, 2, 3}
+    exact = torch.floor(torch.log2(v.double())).clamp(min=0, max=3).long().cpu()
+    print("fp32-vs-exact log2 level differences in the sweep:", int((exact != ref).sum()))
+
+
+def test_full_size_launch_vs_oracle_and_literal(oracle):
+    """The benched kernel instance itself (B=16, C=256, K=16000, 7x7): every RoI of the launch against the literal
+    kernel (bit-exact with the oracle, see above), and a stride-40 sample of the SAME launch against the CPU oracle."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    B, C = 16, 256
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(B, C, 128, 128, generator=g)
+    for dist in ("nuclei", "routed"):
+        rois = synth.proposals(B, 1000, dist)
+        ac = a.cuda()
+        fast = nb.roi_align(ac, rois.cuda(), 7, 0.25, 0)
+        lit = nb.roi_align_levels([ac], rois.cuda(), 7, [0.25], 0, impl="direct")
+        assert fast.shape == (16000, 256, 7, 7)
+        assert (fast - lit).abs().max().item() <= TOL
+        idx = torch.arange(0, 16000, 40)
+        ref = oracle.roi_align(a, rois[idx], 7, 0.25, 0, nthreads=8)
+        assert (fast[idx.cuda()].cpu() - ref).abs().max().item() <= TOL
+        assert torch.equal(lit[idx.cuda()].cpu(), ref)
+    # the 14x14 mask-branch instance (K = 8000 detection slots)
+    rois = synth.proposals(B, 500, "nuclei", seed=3)
+    fast = nb.roi_align(ac, rois.cuda(), 14, 0.25, 0)
+    idx = torch.arange(0, 8000, 40)
+    ref = oracle.roi_align(a, rois[idx], 14, 0.25, 0, nthreads=8)
+    assert (fast[idx.cuda()].cpu() - ref).abs().max().item() <= TOL
+
+
 def test_full_size_linearity_property():
     """BASELINE cfg-2 size (B=16, C=256, K=16000): RoIAlign is linear in the feature map."""
     import nuhtc_b200 as nb

@@ -238,6 +238,116 @@ def test_merge_oracle_equals_naive_greedy(oracle):
     assert len(area) == len(kept) and set(area.tolist()) != set(kept)
 
 
+def _blob_rings(rng, count, size=64):
+    """Contour-shaped rings: smooth non-convex blobs (thresholded sums of Gaussians) traced by the contour oracle,
+    closed like infer_wsi.py:53 does.  Rings the tracer returns with a pinch point (not simple) are dropped."""
+    yy, xx = np.mgrid[0:size, 0:size]
+    rings = []
+    while len(rings) < count:
+        f = np.zeros((size, size))
+        for _ in range(rng.integers(2, 5)):
+            cy, cx = rng.uniform(22, size - 22, 2)
+            sy, sx = rng.uniform(4, 9, 2)
+            f += np.exp(-(((yy - cy) / sy) ** 2 + ((xx - cx) / sx) ** 2))
+        m = (f > 0.55).astype(np.uint8)
+        if m.sum() < 30:
+            continue
+        from oracle import cpu as O
+        r = O.mask2inst(m).reshape(-1, 2).astype(np.float64)
+        if len(r) < 4 or len(np.unique(r[:-1], axis=0)) != len(r) - 1:   # a vertex visited twice: self-touching ring
+            continue
+        rings.append(r)
+    return rings
+
+
+def test_polygon_area_second_anchor_slab_decomposition(oracle):
+    """The trapezoid-identity oracle (whose summation order follows the GPU's 32-lane butterfly) against an independent
+    algorithm -- vertical slab decomposition with the even-odd rule -- on > 1e4 pairs: the duplicated, jittered ellipse
+    contours of the synthetic slide and cv2-style contours of non-convex blobs.  Areas agree to 1e-9 relative and every
+    IoU > 0.05 decision (the only thing the merge consumes) is identical."""
+    from scipy.spatial import cKDTree
+    d = synth.slide_nuclei(24, 24, per_tile=23, seed=31)
+    N = len(d["score"])
+    rings = [d["xy"][d["voff"][i]:d["voff"][i + 1]] for i in range(N)]
+    ctr = np.array([r.mean(0) for r in rings])
+    pairs = sorted(cKDTree(ctr).query_pairs(22.0))
+    rng = np.random.default_rng(7)
+    blobs = _blob_rings(rng, 400)
+    cases = [(rings[i], rings[j]) for i, j in pairs[:9000]]
+    for _ in range(3000):
+        a, b = blobs[rng.integers(len(blobs))], blobs[rng.integers(len(blobs))]
+        cases.append((a, b + rng.integers(-14, 15, 2).astype(np.float64)))
+    assert len(cases) >= 12000
+    overlapping = decided = 0
+    for a, b in cases:
+        t = oracle.poly_inter_area(a, b)
+        s = oracle.poly_inter_area_slab(a, b)
+        aa, ab = oracle.poly_area(a), oracle.poly_area(b)
+        assert abs(t - s) <= 1e-9 * max(1.0, min(aa, ab)), (t, s)
+        if t > 0:
+            overlapping += 1
+            iou_t, iou_s = t / (aa + ab - t), s / (aa + ab - s)
+            if abs(iou_t - 0.05) > 1e-9:       # the contract excludes |IoU - thr| < 1e-9
+                decided += 1
+                assert (iou_t > 0.05) == (iou_s > 0.05)
+    assert overlapping > 6000 and decided > 6000
+
+
+def test_merge_oracle_equals_all_pairs_search_and_slab_area(oracle):
+    """The grid-accelerated oracle against (1) an O(N^2) candidate search (every envelope pair, what STRtree.query
+    yields) and (2) the same greedy loop on the slab-decomposition area, at ~10k and ~170k nuclei."""
+    d = synth.slide_nuclei(16, 16, per_tile=23, seed=11)
+    for strat in ("probability", "area"):
+        ref = oracle.merge_overlap_arrays(d["xy"], d["voff"], d["score"], 0.05, strat)
+        assert np.array_equal(ref, oracle.merge_overlap_arrays_check(d["xy"], d["voff"], d["score"], 0.05, strat, naive=True))
+        assert np.array_equal(ref, oracle.merge_overlap_arrays_check(d["xy"], d["voff"], d["score"], 0.05, strat, naive=True, slab=True))
+    assert 9000 < len(d["score"]) < 11000
+    from _slides import load_case
+    _, d, thr = load_case(1)   # 66 x 66 tiles, the exact-threshold pairs dropped (the two areas round those differently)
+    ref = oracle.merge_overlap_arrays(d["xy"], d["voff"], d["score"], thr)
+    assert np.array_equal(ref, oracle.merge_overlap_arrays_check(d["xy"], d["voff"], d["score"], thr, naive=False, slab=True))
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_merge_golden_hashes(oracle, case):
+    """Committed kept-id hashes at 15k / 170k / 1.7M nuclei (tests/golden/merge_large.json, BASELINE cfg 5): the oracle
+    reproduces them here; tests/test_gpu_merge.py holds the CUDA merge to the same hashes.  No decisive pair of a golden
+    case is closer than 1e-9 to the threshold (the exact 1/20 ties of the raw slides were dropped)."""
+    from _slides import load_case, sha
+    c, d, thr = load_case(case)
+    k, margin, ties = oracle.merge_overlap_arrays_check(d["xy"], d["voff"], d["score"], thr, naive=False, with_margin=True)
+    assert len(ties) == 0 and margin > 1e-9
+    assert len(k) == c["probability"]["kept"] and sha(k.astype(np.int64)) == c["probability"]["kept_ids_sha256"]
+    assert np.array_equal(k, oracle.merge_overlap_arrays(d["xy"], d["voff"], d["score"], thr))
+
+
+def test_threshold_ties_exist_and_are_dropped(oracle):
+    """IoU of integer-vertex rings is rational and does hit 1/20 exactly: the raw 66x66 slide holds such decisive pairs,
+    the slab and trapezoid areas round them to different sides, and drop_threshold_ties removes exactly the nuclei the
+    golden file lists."""
+    from _slides import golden
+    c = golden()["cases"][1]
+    d = synth.slide_nuclei(c["tiles"][0], c["tiles"][1], per_tile=23, seed=c["seed"])
+    _, margin, ties = oracle.merge_overlap_arrays_check(d["xy"], d["voff"], d["score"], 0.05, naive=False, with_margin=True)
+    assert margin < 1e-12 and len(ties) >= 1
+    _, removed = oracle.drop_threshold_ties(d, 0.05)
+    assert removed.tolist() == c["removed_out_of_contract"]
+    assert {int(a) for a, b in ties} | {int(b) for a, b in ties} & set(removed.tolist())
+
+
+def test_golden_cases_hold_no_identical_rings():
+    """Out of contract: the reference keys a dict by the shapely polygon (nuclei_merge.py:101-103), so two
+    nuclei with IDENTICAL rings collide and it keeps the LOWER-scored copy.  The raw synthetic slides do hold a few such
+    twins (4 pairs in 171k nuclei); the golden cases drop the lower-scored copy, like the exact-threshold pairs."""
+    from _slides import load_case
+    raw = synth.slide_nuclei(66, 66, per_tile=23, seed=66)
+    keys = {raw["xy"][raw["voff"][i]:raw["voff"][i + 1]].tobytes() for i in range(len(raw["score"]))}
+    assert len(keys) < len(raw["score"])
+    _, d, _ = load_case(1)
+    keys = {d["xy"][d["voff"][i]:d["voff"][i + 1]].tobytes() for i in range(len(d["score"]))}
+    assert len(keys) == len(d["score"])
+
+
 def test_golden_attention_extractor(oracle):
     """AttentionRoIExtractor.forward executed from the reference source (mmcv RoIAlign layers -> oracle) vs the restatement."""
     z = np.load(os.path.join(G, "attention_extractor.npz"))
