@@ -6,7 +6,8 @@ C ABI of include/nuhtc_b200.h (libnuhtc_b200.so, hand-written CUDA).  GPU only: 
 """
 from . import _lib
 from ._lib import NuhtcError, LIB_PATH
-from .mmcv_ops import RoIAlign, roi_align, nms, batched_nms, roi_align_levels, nms_groups, to_nhwc, clear_layout_cache
+from .mmcv_ops import (RoIAlign, roi_align, nms, batched_nms, roi_align_levels, nms_groups, to_nhwc, to_cg32, clear_layout_cache,
+                       layout_cache, StagedLevels, stage_levels)
 from .mask_paste import _do_paste_mask, paste_masks, get_seg_masks, get_seg_masks_device
 from .mask_nms import mask_nms, mask_nms_device, pack_masks
 from .nuclei_merge import merge_arrays, merge_overlap

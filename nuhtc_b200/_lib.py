@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnuhtc_b200.so")
 
 # constants of include/nuhtc_b200.h
-LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_CG32 = 0, 1, 2
 ROI_ROUTE, ROI_SUM = 0, 1
 IMPL_AUTO, IMPL_DIRECT = 0, 1
 NMS_AGNOSTIC, NMS_OFFSET, NMS_PERCLASS, NMS_PERCLASS_RAW = 0, 1, 2, 3
@@ -31,6 +31,10 @@ SIGNATURES = {
     "nuhtc_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "nuhtc_roi_align_fwd": (_i, [_c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_f), _i, _i, _i, _i, _vp, _i,
                                  _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "nuhtc_to_cg32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nuhtc_roi_align_workspace_bytes": (_sz, [_c.POINTER(_i), _c.POINTER(_i), _i, _i, _i, _i, _i]),
+    "nuhtc_roi_align_cg32": (_i, [_c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_f), _i, _i, _i, _vp, _i, _i, _i, _i,
+                                  _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_attention_pool_workspace_bytes": (_sz, [_i, _i]),
     "nuhtc_attention_pool": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_nms_workspace_bytes": (_sz, [_i64, _i, _i64, _i]),
@@ -99,7 +103,7 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
 # ---- launch accounting: how many of OUR kernels each C-ABI call enqueues (bench.py reports the sum as
 # "gpu_launches"; library kernels such as cub's radix sort are not counted)
 LAUNCHES = {"n": 0}
-KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "attention_pool": 4, "roi_align": 1, "nms": 9, "paste": 2, "paste_dual": 1, "pack": 3, "mask_nms": 8, "merge": 16, "contours": 2, "rings": 1, "glue": 1}
+KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "to_cg32": 1, "roi_align_strip": 5, "attention_pool": 4, "roi_align": 1, "nms": 9, "paste": 2, "paste_dual": 1, "pack": 3, "mask_nms": 8, "merge": 16, "contours": 2, "rings": 1, "glue": 1}
 
 
 def count(op: str, n: int = 1) -> None:

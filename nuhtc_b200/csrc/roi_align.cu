@@ -22,81 +22,8 @@
 #include <string.h>
 
 #include "common.cuh"
-
-struct RoiLevels {
-    const float *data[NUHTC_MAX_LEVELS];
-    int H[NUHTC_MAX_LEVELS];
-    int W[NUHTC_MAX_LEVELS];
-    float scale[NUHTC_MAX_LEVELS];
-    int L;
-};
-
-// SingleRoIExtractor.map_roi_levels (single_level_roi_extractor.py:51-55):
-//   torch.floor(torch.log2(sqrt(w*h)/finest + 1e-6)).clamp(0, L-1)
-// The reference evaluates log2 in fp32, so a value just below a power of two can round UP to the integer and land one
-// level higher than the exact logarithm would put it.  The same fp32 chain is evaluated here: IEEE sub/mul/sqrt/div/add
-// and libdevice log2f, the function ATen's CUDA log2 kernel calls (tests/test_gpu_roi_align.py sweeps every float
-// around the level boundaries against torch.floor(torch.log2(.)) on the device).
-__device__ __forceinline__ int route_level(const float *roi, int L, float finest) {
-    const float s = __fsqrt_rn(__fmul_rn(__fsub_rn(roi[3], roi[1]), __fsub_rn(roi[4], roi[2])));
-    const float v = __fadd_rn(__fdiv_rn(s, finest), 1e-6f);
-    const float f = floorf(log2f(v));   // NaN (negative area) and -inf (v == 0 cannot happen: + 1e-6) clamp to level 0
-    int l = 0;
-    if (f >= 1.0f) l = f >= (float)(L - 1) ? L - 1 : (int)f;
-    return l;
-}
-
-struct RoiGeom {
-    float start_w, start_h, bin_w, bin_h;
-    int gw, gh;
-    float count;
-    int b;
-};
-
-__device__ __forceinline__ RoiGeom roi_geom(const float *roi, float scale, int PH, int PW, int sr, int aligned) {
-    RoiGeom g;
-    const float off = aligned ? 0.5f : 0.0f;
-    g.start_w = __fsub_rn(__fmul_rn(roi[1], scale), off);
-    g.start_h = __fsub_rn(__fmul_rn(roi[2], scale), off);
-    const float ew = __fsub_rn(__fmul_rn(roi[3], scale), off);
-    const float eh = __fsub_rn(__fmul_rn(roi[4], scale), off);
-    float rw = __fsub_rn(ew, g.start_w), rh = __fsub_rn(eh, g.start_h);
-    if (!aligned) {
-        rw = fmaxf(rw, 1.0f);
-        rh = fmaxf(rh, 1.0f);
-    }
-    g.bin_h = __fdiv_rn(rh, (float)PH);
-    g.bin_w = __fdiv_rn(rw, (float)PW);
-    g.gh = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rh, (float)PH));
-    g.gw = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rw, (float)PW));
-    int c = g.gh * g.gw;
-    if (c < 1) c = 1;
-    g.count = (float)c;
-    g.b = (int)roi[0];
-    return g;
-}
-
-// sample coordinate, same association as the CPU reference: (start + p*bin) + ((i+.5)*bin)/g
-__device__ __forceinline__ float sample_coord(float start, float bin, int p, int i, int g) {
-    return __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
-                     __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)g));
-}
-
-// one axis of the bilinear sample: false if the sample is outside (-1, D)
-__device__ __forceinline__ bool axis_sample(float c, int D, int &lo, int &hi, float &l, float &h) {
-    if (c < -1.0f || c > (float)D) return false;
-    if (c <= 0.f) c = 0.f;
-    lo = (int)c;
-    if (lo >= D - 1) {
-        hi = lo = D - 1;
-        c = (float)lo;
-    } else {
-        hi = lo + 1;
-    }
-    l = __fsub_rn(c, (float)lo);
-    h = __fsub_rn(1.0f, l);
-    return true;
-}
+#include "roi_common.cuh"
+#include "roi_strip.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // literal kernel
@@ -164,8 +91,6 @@ __global__ void __launch_bounds__(256) roi_align_direct_kernel(RoiLevels lv, int
 // ---------------------------------------------------------------------------------------------
 // separable fast kernel (NHWC input)
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxTap = 8; // taps per bin per axis held in the tables; larger bins take the literal path
-
 template <int P>
 struct SepCfg {
     static constexpr int PP = P * P;
@@ -173,53 +98,12 @@ struct SepCfg {
     static constexpr int S = (PP % 8 == 1) ? PP : (PP + ((9 - PP % 8) % 8));
 };
 
-// per-axis tap table for bin p: accumulated bilinear weights over the g samples of the bin, each
-// divided by `div` (1 for x, the sample count for y).  n = -1 flags a bin with more than kMaxTap taps.
-__device__ __forceinline__ void build_axis_taps(float start, float bin, int g, int p, int D, float div, float *w, int *first,
-                                                int *n) {
-#pragma unroll
-    for (int j = 0; j < kMaxTap; ++j) w[j] = 0.f;
-    int base = -1, last = -1;
-    bool ok = true;
-    for (int i = 0; i < g; ++i) {
-        const float c = sample_coord(start, bin, p, i, g);
-        int lo, hi;
-        float l, h;
-        if (!axis_sample(c, D, lo, hi, l, h)) continue;
-        if (base < 0) base = lo;
-        const int a = lo - base, b = hi - base;
-        if (b >= kMaxTap) {
-            ok = false;
-            break;
-        }
-        w[a] += h;
-        w[b] += l;
-        last = b;
-    }
-    if (ok && div != 1.0f) {
-#pragma unroll
-        for (int j = 0; j < kMaxTap; ++j) w[j] = __fdiv_rn(w[j], div);
-    }
-    *first = base < 0 ? 0 : base;
-    *n = ok ? last + 1 : -1;
-}
-
-// two fp32 FMAs in one instruction (Blackwell FFMA2): d = a * {b.x, b.y} + c
-__device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
-    unsigned long long ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-    return d;
-}
-
 // One sweep over the window rows [y0, y1) for a thread that owns output column pw (NX x-taps starting at
 // the pointer) and PB output rows: t = sum_j wx[j] * V[y][xs+j] per row, then acc[i] += wy[i][y-ys[i]] * t.
-template <int NX, int PB, int VEC, int QSTRIDE>
-__device__ __forceinline__ void sweep_rows(const float *__restrict__ rowp, size_t rstride, int C, int y0, int y1,
+// pix = float stride between neighbouring pixels (C for NHWC, 32 for the channel-group layout), slice = float stride
+// between the VEC channel slices of a thread.
+template <int NX, int PB, int VEC>
+__device__ __forceinline__ void sweep_rows(const float *__restrict__ rowp, size_t rstride, size_t pix, size_t slice, int y0, int y1,
                                            const float *__restrict__ s_wxp, const float *__restrict__ s_wyp, const int (&ys)[PB],
                                            const int (&ny)[PB], float2 (&acc)[PB][VEC][2], int nx_rt = 0) {
     constexpr int NXR = NX > 0 ? NX : 1;
@@ -240,7 +124,7 @@ __device__ __forceinline__ void sweep_rows(const float *__restrict__ rowp, size_
 #pragma unroll
             for (int j = 0; j < NX; ++j)
 #pragma unroll
-                for (int u = 0; u < VEC; ++u) v[j][u] = ldg_f4(rowp + (size_t)j * C + u * QSTRIDE);
+                for (int u = 0; u < VEC; ++u) v[j][u] = ldg_f4(rowp + (size_t)j * pix + u * slice);
 #pragma unroll
             for (int j = 0; j < NX; ++j)
 #pragma unroll
@@ -255,7 +139,7 @@ __device__ __forceinline__ void sweep_rows(const float *__restrict__ rowp, size_
                 const float w = s_wxp[j];
 #pragma unroll
                 for (int u = 0; u < VEC; ++u) {
-                    const float4 vv = ldg_f4(rowp + (size_t)j * C + u * QSTRIDE);
+                    const float4 vv = ldg_f4(rowp + (size_t)j * pix + u * slice);
                     t[u][0] = ffma2(w, make_float2(vv.x, vv.y), t[u][0]);
                     t[u][1] = ffma2(w, make_float2(vv.z, vv.w), t[u][1]);
                 }
@@ -281,7 +165,9 @@ __device__ __forceinline__ void sweep_rows(const float *__restrict__ rowp, size_
 template <int P, int NQ, int PHS, int VEC, int MINB>
 __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int sr,
                                                                     int aligned, int mode, float finest,
-                                                                    float *__restrict__ out, const float *__restrict__ bias) {
+                                                                    float *__restrict__ out, const float *__restrict__ bias,
+                                                                    int cg32, const int *__restrict__ list,
+                                                                    const int *__restrict__ list_count) {
     constexpr int CC = NQ * 4 * VEC;
     constexpr int PP = SepCfg<P>::PP;
     constexpr int S = SepCfg<P>::S;
@@ -299,7 +185,11 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
     int *s_ny = s_ys + P;
     int *s_meta = s_ny + P;              // [0] level, [1] batch index
 
-    const int k = blockIdx.x;
+    // with a RoI list (the strip kernel's leftovers: windows too large to stage) a small grid walks the device-side list
+    const int n_items = list ? *list_count : (int)gridDim.x;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    if (item != (int)blockIdx.x) __syncthreads();   // the previous item's tile and tables are still being read
+    const int k = list ? list[item] : item;
     const int c0 = blockIdx.y * CC;
     const int tid = threadIdx.x;
     const int q = tid % NQ;
@@ -350,18 +240,24 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
                 y1 = max(y1, ys[i] + ny[i]);
             }
         }
-        const float *img = lv.data[l] + (size_t)b * H * W * C + c0 + 4 * q;
+        // NHWC: [b][y][x][C]; channel-group layout: [b][C/32][y][x][32] (the thread's quad never straddles a group)
+        const int cq = c0 + 4 * q;
+        const size_t plane = (size_t)H * W * 32;
+        const size_t pix = cg32 ? 32 : (size_t)C;
+        const size_t slice = cg32 ? (size_t)(NQ * 4 / 32) * plane : (size_t)NQ * 4;
+        const float *img = cg32 ? lv.data[l] + (size_t)b * H * W * C + (size_t)(cq >> 5) * plane + (cq & 31)
+                                : lv.data[l] + (size_t)b * H * W * C + cq;
         if (!slow) {
             if (nx > 0 && y1 > y0) {
-                const float *rowp = img + ((size_t)y0 * W + s_xs[pw]) * (size_t)C;
-                const size_t rstride = (size_t)W * C;
+                const float *rowp = img + ((size_t)y0 * W + s_xs[pw]) * pix;
+                const size_t rstride = (size_t)W * pix;
                 const float *wxp = s_wx + pw * kMaxTap, *wyp = s_wy + ph0 * kMaxTap;
                 switch (nx) {
-                    case 1: sweep_rows<1, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
-                    case 2: sweep_rows<2, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
-                    case 3: sweep_rows<3, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
-                    case 4: sweep_rows<4, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc); break;
-                    default: sweep_rows<0, PB, VEC, NQ * 4>(rowp, rstride, C, y0, y1, wxp, wyp, ys, ny, acc, nx); break;
+                    case 1: sweep_rows<1, PB, VEC>(rowp, rstride, pix, slice, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    case 2: sweep_rows<2, PB, VEC>(rowp, rstride, pix, slice, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    case 3: sweep_rows<3, PB, VEC>(rowp, rstride, pix, slice, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    case 4: sweep_rows<4, PB, VEC>(rowp, rstride, pix, slice, y0, y1, wxp, wyp, ys, ny, acc); break;
+                    default: sweep_rows<0, PB, VEC>(rowp, rstride, pix, slice, y0, y1, wxp, wyp, ys, ny, acc, nx); break;
                 }
             }
         } else {
@@ -385,9 +281,9 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
                         const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
 #pragma unroll
                         for (int u = 0; u < VEC; ++u) {
-                            const float *pu = img + u * NQ * 4;
-                            const float4 v1 = ldg_f4(pu + ((size_t)yl * W + xl) * C), v2 = ldg_f4(pu + ((size_t)yl * W + xh) * C);
-                            const float4 v3 = ldg_f4(pu + ((size_t)yh * W + xl) * C), v4 = ldg_f4(pu + ((size_t)yh * W + xh) * C);
+                            const float *pu = img + u * slice;
+                            const float4 v1 = ldg_f4(pu + ((size_t)yl * W + xl) * pix), v2 = ldg_f4(pu + ((size_t)yl * W + xh) * pix);
+                            const float4 v3 = ldg_f4(pu + ((size_t)yh * W + xl) * pix), v4 = ldg_f4(pu + ((size_t)yh * W + xh) * pix);
                             a[u][0] += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
                             a[u][1] += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
                             a[u][2] += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
@@ -454,6 +350,7 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
         }
         st_stream_f4(outp + 4 * i, v);
     }
+    }   // item loop
 }
 
 template <int P, int NQ, int VEC>
@@ -463,7 +360,8 @@ static size_t sep_smem_bytes() {
 
 template <int P, int NQ, int PHS, int VEC, int MINB>
 static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
-                      float *out, const float *bias, cudaStream_t st) {
+                      float *out, const float *bias, cudaStream_t st, int cg32 = 0, const int *list = nullptr,
+                      const int *list_count = nullptr) {
     static bool attr_done[kNuhtcMaxDevices] = {false};
     const int dev = nuhtc_device();
     const size_t smem = sep_smem_bytes<P, NQ, VEC>();
@@ -471,8 +369,11 @@ static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int 
         NUHTC_CUDA(cudaFuncSetAttribute(roi_align_sep_kernel<P, NQ, PHS, VEC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev] = true;
     }
-    dim3 grid(K, C / (NQ * 4 * VEC));
-    roi_align_sep_kernel<P, NQ, PHS, VEC, MINB><<<grid, NQ * P * PHS, smem, st>>>(lv, C, rois, sr, aligned, mode, finest, out, bias);
+    // every RoI: one CTA each; a RoI list: a resident grid that walks the list (its length is only known on the device)
+    const int gx = list ? (K < 4 * nuhtc_sm_count() ? K : 4 * nuhtc_sm_count()) : K;
+    dim3 grid(gx, C / (NQ * 4 * VEC));
+    roi_align_sep_kernel<P, NQ, PHS, VEC, MINB><<<grid, NQ * P * PHS, smem, st>>>(lv, C, rois, sr, aligned, mode, finest, out, bias,
+                                                                                  cg32, list, list_count);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }
@@ -487,35 +388,6 @@ static int launch_sep(const RoiLevels &lv, int C, const float *rois, int K, int 
 // warps wait on the row's "full" barrier, take their taps with conflict-free LDS.128, and release the
 // row to the producer through its "empty" barrier.  Window rows wider than the ring stage, or bins with
 // more than kMaxTap taps, fall back to the direct global-load sweep of the v2 kernel inside the same CTA.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
 constexpr int kPipeMaxRows = 40; // staged windows taller than this take the direct path
 
 // 2-D TMA tensor maps of the NHWC levels: dim0 = channels, dim1 = pixels (B*H*W); box = {CC channels, WBOX pixels}.
@@ -549,13 +421,6 @@ struct PipeSlot { // tap tables + geometry of one work item
 
 enum { kPipeStaged = 0, kPipeDirect = 1, kPipeLiteral = 2 };
 constexpr int kPipeSlots = 4;
-
-__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // position in the row ring: stage index and the parity of its current use
 struct RingPos {
@@ -893,7 +758,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                     if (md == kPipeDirect) {
                         if (nx > 0 && my1 > my0) {
                             const float *rowp = img + ((size_t)my0 * W + sl.xs[pw]) * (size_t)C;
-                            sweep_rows<0, PB, 1, NQ * 4>(rowp, (size_t)W * C, C, my0, my1, wxp, wyp, ys, ny, acc, nx);
+                            sweep_rows<0, PB, 1>(rowp, (size_t)W * C, (size_t)C, 0, my0, my1, wxp, wyp, ys, ny, acc, nx);
                         }
                     } else {
                         const float *roi = rois + (size_t)k * 5;
@@ -1113,6 +978,66 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
     return NUHTC_OK;
 }
 
+
+// per-RoI kernel on the channel-group layout: every RoI (list == nullptr) or the RoIs of a device-side list
+static int launch_sep_cg32(const RoiLevels &lv, int C, const float *rois, int K, int P, int sr, int aligned, int mode,
+                           float finest, float *out, const float *bias, cudaStream_t st, const int *list,
+                           const int *list_count) {
+    if (P == 7) {
+        if (C % 256 == 0) return launch_sep<7, 32, 1, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+        if (C % 128 == 0) return launch_sep<7, 16, 1, 2, 4>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+        if (C % 64 == 0) return launch_sep<7, 16, 1, 1, 8>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+        return launch_sep<7, 8, 1, 1, 8>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+    }
+    if (C % 64 == 0) return launch_sep<14, 8, 2, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+    return launch_sep<14, 8, 2, 1, 2>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+}
+
+NUHTC_API size_t nuhtc_roi_align_workspace_bytes(const int *H, const int *W, int L, int B, int K, int PH, int PW) {
+    if (L < 1 || L > NUHTC_MAX_LEVELS || !H || !W || PH != PW || (PH != 7 && PH != 14) || K <= 0) return 256;
+    return roi_strip_workspace_bytes(H, W, L, B, K, PH);
+}
+
+NUHTC_API int nuhtc_to_cg32(const float *in, float *out, int B, int C, int H, int W, int channels_last, void *stream) {
+    NUHTC_CHECK_ARG(B >= 0 && C >= 32 && C % 32 == 0 && H >= 1 && W >= 1, "to_cg32: bad sizes (C must be a multiple of 32)");
+    if (B == 0) return NUHTC_OK;
+    NUHTC_CHECK_ARG(in && out && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0), "to_cg32: null or misaligned pointer");
+    NUHTC_CHECK_ARG(channels_last || (H * W) % 4 == 0, "to_cg32: H*W must be a multiple of 4 for an NCHW source");
+    NUHTC_CHECK_ARG(C / 32 <= 65535 && B <= 65535, "to_cg32: C or B too large");
+    return roi_to_cg32(in, out, B, C, H, W, channels_last, (cudaStream_t)stream);
+}
+
+NUHTC_API int nuhtc_roi_align_cg32(const float *const *feats, const int *H, const int *W, const float *scale, int L, int B,
+                                   int C, const float *rois, int K, int PH, int PW, int sampling_ratio, int aligned, int mode,
+                                   float finest_scale, float *out, const float *bias, void *ws, size_t ws_bytes, void *stream) {
+    NUHTC_CHECK_ARG(L >= 1 && L <= NUHTC_MAX_LEVELS, "roi_align_cg32: L=%d out of range", L);
+    NUHTC_CHECK_ARG(PH == PW && (PH == 7 || PH == 14) && C >= 32 && C % 32 == 0 && B >= 0 && K >= 0,
+                    "roi_align_cg32: needs PH == PW in {7, 14} and C %% 32 == 0 (PH=%d PW=%d C=%d)", PH, PW, C);
+    NUHTC_CHECK_ARG(mode == NUHTC_ROI_ROUTE || mode == NUHTC_ROI_SUM, "roi_align_cg32: bad mode %d", mode);
+    NUHTC_CHECK_ARG(finest_scale > 0.f || L == 1 || mode == NUHTC_ROI_SUM, "roi_align_cg32: finest_scale must be > 0");
+    if (K == 0) return NUHTC_OK;
+    NUHTC_CHECK_ARG(feats && H && W && scale && rois && out, "roi_align_cg32: null pointer");
+    RoiLevels lv;
+    lv.L = L;
+    for (int l = 0; l < L; ++l) {
+        NUHTC_CHECK_ARG(feats[l] != nullptr && H[l] >= 1 && W[l] >= 1 && ((uintptr_t)feats[l] % 128 == 0), "roi_align_cg32: bad level %d", l);
+        lv.data[l] = feats[l];
+        lv.H[l] = H[l];
+        lv.W[l] = W[l];
+        lv.scale[l] = scale[l];
+    }
+    NUHTC_CHECK_ARG((uintptr_t)out % 16 == 0, "roi_align_cg32: out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    static const bool no_strip = getenv("NUHTC_RA_STRIP") && getenv("NUHTC_RA_STRIP")[0] == '0';   // A/B: per-RoI kernel only
+    if (roi_strip_supported(C, PH, PW, mode, L) && !no_strip) {
+        const int *left = nullptr, *left_count = nullptr;
+        const int rc = roi_strip_forward(lv, B, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, ws, ws_bytes,
+                                         st, &left, &left_count);
+        if (rc != NUHTC_OK) return rc;
+        return launch_sep_cg32(lv, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, left, left_count);
+    }
+    return launch_sep_cg32(lv, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, nullptr, nullptr);
+}
 
 // ---------------------------------------------------------------------------------------------
 // NCHW -> NHWC (once per level per batch; HBM-bound transpose through a padded smem tile)

@@ -21,7 +21,8 @@ import torch.nn as nn
 
 from . import _lib as L
 
-__all__ = ["RoIAlign", "roi_align", "nms", "batched_nms", "roi_align_levels", "to_nhwc", "clear_layout_cache",
+__all__ = ["RoIAlign", "roi_align", "nms", "batched_nms", "roi_align_levels", "to_nhwc", "to_cg32", "clear_layout_cache",
+           "layout_cache", "StagedLevels", "stage_levels",
            "nms_groups", "attention_pool"]
 
 
@@ -33,18 +34,54 @@ def _pair(x) -> Tuple[int, int]:
 
 
 # ----------------------------------------------------------------------------- layout staging
-# The RoIAlign gather wants channel-contiguous (NHWC) levels.  A level that arrives NCHW-contiguous
-# is re-laid out once by our own transpose kernel and remembered while the source tensor is alive
-# and unmodified (the three cascade stages and the mask branch pool from the same FPN outputs).
+# The RoIAlign kernels want the channel axis contiguous.  A level that arrives NCHW is re-laid out by our own kernels:
+#   * CG32  [B][C/32][H][W][32]  -- the strip-shared kernels (7x7 / 14x14 outputs, C % 32 == 0): nuhtc_to_cg32
+#   * NHWC  [B][H][W][C]         -- the attention pooling and the round-1 per-RoI kernels: nuhtc_nchw_to_nhwc
+# Staging is done ONCE per batch by whoever owns the batch (RoIStage.run, the RoI extractors: `stage_levels`) and the
+# staged buffers are passed down explicitly.  An optional cache keyed on (data_ptr, _version, shape) exists for callers
+# that go through the per-level mmcv surface (RoIAlign.forward is called level by level, stage by stage); it is OFF by
+# default and is never consulted while a CUDA graph is being captured, because `_version` does not see writes made by
+# graph replays, by raw-pointer writers or by fresh tensor objects on recycled storage (a stale layout would be silent).
 _LAYOUT_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
-_LAYOUT_CACHE_MAX = 8
+_LAYOUT_CACHE_MAX = 16
+_LAYOUT_CACHE_ON = [False]
 
 
 def clear_layout_cache() -> None:
     _LAYOUT_CACHE.clear()
 
 
-def to_nhwc(x: torch.Tensor, cache: bool = True) -> torch.Tensor:
+class layout_cache:
+    """``with layout_cache():`` -- remember staged layouts of unmodified source tensors inside the block (e.g. around one
+    forward pass that calls RoIAlign level by level).  The caller vouches that the features are only written through
+    torch ops on tensors it holds (see the hazard note above); the cache is emptied on exit."""
+
+    def __enter__(self):
+        self.prev = _LAYOUT_CACHE_ON[0]
+        _LAYOUT_CACHE_ON[0] = True
+        return self
+
+    def __exit__(self, *a):
+        _LAYOUT_CACHE_ON[0] = self.prev
+        if not self.prev:
+            clear_layout_cache()
+
+
+def _cached(x: torch.Tensor, kind: str, make):
+    use = _LAYOUT_CACHE_ON[0] and not torch.cuda.is_current_stream_capturing()
+    key = (kind, x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), x.device.index)
+    if use and key in _LAYOUT_CACHE:
+        _LAYOUT_CACHE.move_to_end(key)
+        return _LAYOUT_CACHE[key][1]
+    out = make()
+    if use:
+        _LAYOUT_CACHE[key] = (x, out)  # holding `x` keeps its storage (and so the key) from being recycled
+        while len(_LAYOUT_CACHE) > _LAYOUT_CACHE_MAX:
+            _LAYOUT_CACHE.popitem(last=False)
+    return out
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
     """[B,C,H,W] fp32 CUDA (any strides) -> contiguous [B,H,W,C] buffer (returned as a [B,H,W,C] tensor)."""
     L.require_cuda(x, "input")
     assert x.dim() == 4 and x.dtype == torch.float32, "expected a 4-D fp32 feature map"
@@ -53,43 +90,95 @@ def to_nhwc(x: torch.Tensor, cache: bool = True) -> torch.Tensor:
         return x.permute(0, 2, 3, 1)
     if not x.is_contiguous():
         x = x.contiguous()
-    key = (x.data_ptr(), x._version, tuple(x.shape), x.device.index)
-    if cache and key in _LAYOUT_CACHE:
-        _LAYOUT_CACHE.move_to_end(key)
-        return _LAYOUT_CACHE[key][1]
-    out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        L.check(L.lib().nuhtc_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C, H, W, L.stream_ptr(x.device)), "nchw_to_nhwc")
-    L.count("nchw_to_nhwc")
-    if cache:
-        _LAYOUT_CACHE[key] = (x, out)  # holding `x` keeps its storage (and so the key) from being recycled
-        while len(_LAYOUT_CACHE) > _LAYOUT_CACHE_MAX:
-            _LAYOUT_CACHE.popitem(last=False)
-    return out
+
+    def make():
+        out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nuhtc_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C, H, W, L.stream_ptr(x.device)), "nchw_to_nhwc")
+        L.count("nchw_to_nhwc")
+        return out
+    return _cached(x, "nhwc", make)
+
+
+def to_cg32(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 CUDA, C % 32 == 0 (NCHW-contiguous or channels_last) -> [B, C/32, H, W, 32] buffer."""
+    L.require_cuda(x, "input")
+    assert x.dim() == 4 and x.dtype == torch.float32, "expected a 4-D fp32 feature map"
+    B, C, H, W = x.shape
+    assert C % 32 == 0
+    cl = x.permute(0, 2, 3, 1).is_contiguous() and not x.is_contiguous()
+    if not cl and (not x.is_contiguous() or (H * W) % 4 != 0):
+        x = x.contiguous(memory_format=torch.channels_last)   # odd map sizes: go through the line-permutation kernel
+        cl = True
+
+    def make():
+        out = torch.empty((B, C // 32, H, W, 32), dtype=torch.float32, device=x.device)
+        if B > 0:
+            with torch.cuda.device(x.device):
+                L.check(L.lib().nuhtc_to_cg32(x.data_ptr(), out.data_ptr(), B, C, H, W, int(cl), L.stream_ptr(x.device)), "to_cg32")
+            L.count("to_cg32")
+        return out
+    return _cached(x, "cg32", make)
 
 
 def _fast_path_ok(C: int, ph: int, pw: int) -> bool:
-    return ph == pw and ph in (7, 14) and C % 64 == 0
+    return ph == pw and ph in (7, 14) and C % 32 == 0
 
 
-def roi_align_levels(feats: Sequence[torch.Tensor], rois: torch.Tensor, output_size, spatial_scales: Sequence[float],
+class StagedLevels:
+    """FPN levels of one batch, laid out for the RoIAlign kernels.  Build it once per batch with ``stage_levels`` and pass
+    it wherever ``feats`` is accepted: the three cascade stages and the mask branch then share one re-layout."""
+
+    def __init__(self, feats: Sequence[torch.Tensor]):
+        f0 = feats[0]
+        self.B, self.C = int(f0.shape[0]), int(f0.shape[1])
+        self.shapes = [(int(f.shape[2]), int(f.shape[3])) for f in feats]
+        self.device = f0.device
+        for f in feats:
+            L.require_cuda(f, "feats")
+            assert f.dtype == torch.float32 and f.shape[0] == self.B and f.shape[1] == self.C
+        self.nchw = list(feats)
+        self.cg32 = [to_cg32(f) for f in feats] if self.C % 32 == 0 else None
+
+    def __len__(self):
+        return len(self.nchw)
+
+    def sub(self, idx: Sequence[int]) -> "StagedLevels":
+        o = object.__new__(StagedLevels)
+        o.B, o.C, o.device = self.B, self.C, self.device
+        o.shapes = [self.shapes[i] for i in idx]
+        o.nchw = [self.nchw[i] for i in idx]
+        o.cg32 = None if self.cg32 is None else [self.cg32[i] for i in idx]
+        return o
+
+
+def stage_levels(feats) -> StagedLevels:
+    return feats if isinstance(feats, StagedLevels) else StagedLevels(list(feats))
+
+
+def roi_align_levels(feats, rois: torch.Tensor, output_size, spatial_scales: Sequence[float],
                      sampling_ratio: int = 0, aligned: bool = True, mode: str = "route", finest_scale: float = 56.0,
                      impl: str = "auto", out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """All FPN levels in ONE launch.
+    """All FPN levels in ONE call.
 
     mode 'route': each RoI is pooled on the level SingleRoIExtractor.map_roi_levels picks
                   (single_level_roi_extractor.py:36-55); one level = plain roi_align.
     mode 'sum'  : every RoI is pooled on every level, results summed in level order
                   (AttentionRoIExtractor's RoIAlign branch, roi_extractors_cus.py:213-218,246).
-    feats: NCHW fp32 CUDA tensors [B,C,H_l,W_l] (NCHW-contiguous or channels_last)."""
+    feats: NCHW fp32 CUDA tensors [B,C,H_l,W_l] (NCHW-contiguous or channels_last), or a ``StagedLevels``.
+    impl : 'auto' (strip-shared kernels on the CG32 layout when the shape allows, else the literal kernel),
+           'direct' (literal per-sample kernel, bit-exact with the reference's accumulation order),
+           'nhwc' (round-1 per-RoI kernels on the NHWC layout; kept for A/B measurements)."""
     ph, pw = _pair(output_size)
+    staged = feats if isinstance(feats, StagedLevels) else None
     nl = len(feats)
     assert 1 <= nl <= L.MAX_LEVELS and len(spatial_scales) == nl
     L.require_cuda(rois, "rois")
     assert rois.dim() == 2 and rois.size(1) == 5, "rois must have shape [K,5]"
-    B, C = feats[0].shape[0], feats[0].shape[1]
+    raw = staged.nchw if staged is not None else list(feats)
+    B, C = raw[0].shape[0], raw[0].shape[1]
     K = rois.size(0)
-    dev = feats[0].device
+    dev = raw[0].device
     rois = rois.to(torch.float32).contiguous()
     if out is None:
         out = torch.empty((K, C, ph, pw), dtype=torch.float32, device=dev)
@@ -100,26 +189,35 @@ def roi_align_levels(feats: Sequence[torch.Tensor], rois: torch.Tensor, output_s
     if bias is not None:
         assert bias.shape == (K, C) and bias.dtype == torch.float32 and bias.is_cuda
         bias = bias.contiguous()
-    use_fast = impl == "auto" and _fast_path_ok(C, ph, pw)
-    bufs = []
-    for f in feats:
+    for f in raw:
         L.require_cuda(f, "feats")
         assert f.dtype == torch.float32 and f.shape[0] == B and f.shape[1] == C
-        if use_fast:
-            bufs.append(to_nhwc(f))
-        else:
-            bufs.append(f if f.is_contiguous() else f.contiguous())
-    layout = L.LAYOUT_NHWC if use_fast else L.LAYOUT_NCHW
-    ptrs = (ctypes.c_void_p * nl)(*[b.data_ptr() for b in bufs])
-    Hs = (ctypes.c_int * nl)(*[int(f.shape[2]) for f in feats])
-    Ws = (ctypes.c_int * nl)(*[int(f.shape[3]) for f in feats])
+    Hs = (ctypes.c_int * nl)(*[int(f.shape[2]) for f in raw])
+    Ws = (ctypes.c_int * nl)(*[int(f.shape[3]) for f in raw])
     sc = (ctypes.c_float * nl)(*[float(s) for s in spatial_scales])
     m = {"route": L.ROI_ROUTE, "sum": L.ROI_SUM}[mode]
+    lib = L.lib()
+    if impl == "auto" and _fast_path_ok(C, ph, pw):
+        bufs = staged.cg32 if staged is not None else [to_cg32(f) for f in raw]
+        ptrs = (ctypes.c_void_p * nl)(*[b.data_ptr() for b in bufs])
+        wsb = lib.nuhtc_roi_align_workspace_bytes(Hs, Ws, nl, B, K, ph, pw)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.nuhtc_roi_align_cg32(ptrs, Hs, Ws, sc, nl, B, C, rois.data_ptr(), K, ph, pw, int(sampling_ratio),
+                                          int(bool(aligned)), m, float(finest_scale), out.data_ptr(), L.ptr(bias), ws.data_ptr(),
+                                          wsb, L.stream_ptr(dev))
+        L.check(rc, "roi_align_cg32")
+        L.count("roi_align_strip")
+        return out
+    use_nhwc = impl == "nhwc" and ph == pw and ph in (7, 14) and C % 64 == 0
+    bufs = [to_nhwc(f) for f in raw] if use_nhwc else [f if f.is_contiguous() else f.contiguous() for f in raw]
+    layout = L.LAYOUT_NHWC if use_nhwc else L.LAYOUT_NCHW
+    ptrs = (ctypes.c_void_p * nl)(*[b.data_ptr() for b in bufs])
     with torch.cuda.device(dev):
-        rc = L.lib().nuhtc_roi_align_fwd(ptrs, Hs, Ws, sc, nl, B, C, layout, rois.data_ptr(), K, ph, pw, int(sampling_ratio),
-                                         int(bool(aligned)), m, float(finest_scale),
-                                         L.IMPL_AUTO if use_fast else L.IMPL_DIRECT, out.data_ptr(), L.ptr(bias),
-                                         L.stream_ptr(dev))
+        rc = lib.nuhtc_roi_align_fwd(ptrs, Hs, Ws, sc, nl, B, C, layout, rois.data_ptr(), K, ph, pw, int(sampling_ratio),
+                                     int(bool(aligned)), m, float(finest_scale),
+                                     L.IMPL_AUTO if use_nhwc else L.IMPL_DIRECT, out.data_ptr(), L.ptr(bias),
+                                     L.stream_ptr(dev))
     L.check(rc, "roi_align_fwd")
     L.count("roi_align")
     return out

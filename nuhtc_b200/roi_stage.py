@@ -22,7 +22,7 @@ from . import det_ops
 from .contours import mask_contours
 from .mask_nms import mask_nms_device
 from .mask_paste import paste_masks, paste_masks_dense_bits
-from .mmcv_ops import nms_groups, roi_align_levels
+from .mmcv_ops import StagedLevels, nms_groups, roi_align_levels, stage_levels
 
 __all__ = ["RoIStageConfig", "RoIStage", "RoIStageResult", "delta2bbox", "bbox2roi"]
 
@@ -184,23 +184,28 @@ class RoIStage:
                 self.trace.setdefault(k, []).append(v)
 
     # -- RoI extractors: one launch over all levels -------------------------------------------------------
-    def extract(self, feats: Sequence[torch.Tensor], rois: torch.Tensor, out_size: int, sampling_ratio: int) -> torch.Tensor:
+    def extract(self, feats: StagedLevels, rois: torch.Tensor, out_size: int, sampling_ratio: int) -> torch.Tensor:
         cfg = self.cfg
         if cfg.extractor == "single":
-            lv = list(feats[: len(cfg.featmap_strides)])
-            return roi_align_levels(lv, rois, out_size, [1.0 / s for s in cfg.featmap_strides[: len(lv)]], sampling_ratio,
+            n = min(len(feats), len(cfg.featmap_strides))
+            lv = feats.sub(range(n))
+            return roi_align_levels(lv, rois, out_size, [1.0 / s for s in cfg.featmap_strides[:n]], sampling_ratio,
                                     True, mode="route", finest_scale=cfg.finest_scale)
         if cfg.extractor == "sum":
-            lv = list(feats[: cfg.sum_levels])
+            lv = feats.sub(range(cfg.sum_levels))
             return roi_align_levels(lv, rois, out_size, [1.0 / s for s in cfg.featmap_strides[: cfg.sum_levels]],
                                     sampling_ratio, True, mode="sum")
         raise ValueError(cfg.extractor)
 
     # -- the stage ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def run(self, feats: Sequence[torch.Tensor], rois: torch.Tensor, max_rois_per_tile: Optional[int] = None) -> RoIStageResult:
+    def run(self, feats, rois: torch.Tensor, max_rois_per_tile: Optional[int] = None) -> RoIStageResult:
+        """feats: the FPN levels of the batch ([B,C,H_l,W_l] fp32 CUDA tensors) or an already staged ``StagedLevels``.
+        The kernel layout is staged ONCE here and handed to the four RoIAlign calls explicitly (no cache involved)."""
         cfg = self.cfg
-        B = feats[0].shape[0]
+        with self._t("stage_layout"):
+            feats = stage_levels(feats)
+        B = feats.B
         dev = rois.device
         K = rois.shape[0]
         C = cfg.num_classes

@@ -105,7 +105,8 @@ def _kernel_levels(rois, impl="auto", C=64, frame=512):
     feats = [torch.full((1, C, frame // s, frame // s), float(l + 1), device="cuda") for l, s in enumerate((4, 8, 16, 32))]
     out = nb.roi_align_levels(feats, rois.cuda(), 7, [1 / 4, 1 / 8, 1 / 16, 1 / 32], 2, mode="route", finest_scale=56, impl=impl)
     lv = out[:, 0, 3, 3].round().long() - 1
-    assert torch.equal(out, (lv + 1).float()[:, None, None, None].expand_as(out))
+    # a bin of a constant map is that constant times a sum of bilinear weights (1 up to fp32 rounding)
+    assert (out - (lv + 1).float()[:, None, None, None]).abs().max().item() < 1e-4
     return lv.cpu()
 
 
@@ -128,7 +129,7 @@ def test_routing_matches_golden_levels(impl):
 def test_routing_at_level_boundaries_every_float(impl):
     """map_roi_levels is floor(log2(v)) evaluated in fp32, so just below a power of two the logarithm can round up to the
     integer.  Sweep +-3000 consecutive floats of the box side around each boundary (v = 2, 4, 8) and compare the kernel's
-    level with the reference expression evaluated by torch on the same device."""
+    level with the reference expression evaluated by torch on the CPU (the contract: the reference's CPU path)."""
     rows = []
     for k in (1, 2, 3):
         side0 = torch.tensor(56.0 * (2.0 ** k - 1e-6), dtype=torch.float32)
@@ -139,16 +140,19 @@ def test_routing_at_level_boundaries_every_float(impl):
         # rectangles: sqrt(w*h) falls between representable sides
         rows.append(torch.stack([torch.zeros_like(side), x1, x1, x1 + side, x1 + side0.expand_as(side).clone()], 1))
     rois = torch.cat(rows).contiguous()
-    r = rois.cuda()
-    scale = torch.sqrt((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]))
-    v = scale / 56 + 1e-6
-    ref = torch.floor(torch.log2(v)).clamp(min=0, max=3).long().cpu()     # single_level_roi_extractor.py:51-55 on the device
+
+    def levels(r):   # single_level_roi_extractor.py:51-55
+        scale = torch.sqrt((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]))
+        return torch.floor(torch.log2(scale / 56 + 1e-6)).clamp(min=0, max=3).long()
+    ref = levels(rois)
     got = _kernel_levels(rois, impl)
     assert torch.equal(got, ref)
-    # the sweep really crosses each boundary, and holds values whose fp32 log2 rounds up across it
     assert set(ref.tolist()) == {0, 1, 2, 3}
-    exact = torch.floor(torch.log2(v.double())).clamp(min=0, max=3).long().cpu()
-    print("fp32-vs-exact log2 level differences in the sweep:", int((exact != ref).sum()))
+    v = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2])) / 56 + 1e-6
+    exact = torch.floor(torch.log2(v.double())).clamp(min=0, max=3).long()
+    dev = levels(rois.cuda()).cpu()
+    print(f"routing sweep ({len(rois)} boxes): fp32-log2 level != exact-log2 level on {int((exact != ref).sum())}; "
+          f"the reference's own CUDA evaluation differs from its CPU evaluation on {int((dev != ref).sum())}")
 
 
 def test_full_size_launch_vs_oracle_and_literal(oracle):

@@ -44,6 +44,17 @@ def test_golden_roi_levels(oracle):
     assert set(np.unique(z["levels"])) == {0, 1, 2, 3}
 
 
+def test_cpu_log2_is_correctly_rounded_near_level_boundaries():
+    """The kernels route with float(log2(double(v))) (roi_common.cuh:route_level); that equals torch's CPU log2 -- the
+    reference's map_roi_levels on the CPU path -- on every float within +-200 000 ulps of the level boundaries."""
+    for k in (1, 2, 3):
+        c = torch.tensor(2.0 ** k, dtype=torch.float32)
+        v = (c.view(torch.int32) + torch.arange(-200000, 200001, dtype=torch.int32)).view(torch.float32)
+        assert torch.equal(torch.floor(torch.log2(v)), torch.floor(torch.log2(v.double()).float()))
+    v = torch.nextafter(torch.tensor(8.0), torch.tensor(0.0))
+    assert float(torch.floor(torch.log2(v))) == 3.0   # the fp32 logarithm rounds up across the boundary
+
+
 def test_golden_multiclass_nms(oracle):
     z = np.load(os.path.join(G, "multiclass_nms.npz"))
     dets, labels, _ = oracle.multiclass_nms(torch.from_numpy(z["boxes"]), torch.from_numpy(z["scores"]), 0.35,

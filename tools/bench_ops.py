@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=16)
     ap.add_argument("--tag", default="")
     ap.add_argument("--only", default="")
+    ap.add_argument("--impl", default="auto", choices=["auto", "nhwc"], help="RoIAlign path: strip-shared (CG32) or round-1 per-RoI (NHWC)")
     a = ap.parse_args()
     peak = 6550.7
     try:
@@ -46,8 +47,11 @@ def main():
     B, C = a.tiles, a.channels
     dev = "cuda"
     feats = [f.to(dev) for f in synth.fpn_levels(B, C)]
-    nhwc = [nb.to_nhwc(f, cache=False) for f in feats]
-    nchw_cl = [n.permute(0, 3, 1, 2) for n in nhwc]  # channels_last views: no staging inside the timed call
+    if a.impl == "auto":
+        nchw_cl = nb.stage_levels(feats)            # staged once: no layout work inside the timed call
+    else:
+        nhwc = [nb.to_nhwc(f) for f in feats]
+        nchw_cl = [n.permute(0, 3, 1, 2) for n in nhwc]  # channels_last views: no staging inside the timed call
     scales = [1 / s for s in synth.FPN_STRIDES]
     out = []
 
@@ -69,19 +73,21 @@ def main():
             if not want(f"roi_align_{P}"):
                 continue
             o = torch.empty(K, C, P, P, device=dev)
-            ms, best = timeit(lambda: nb.roi_align_levels(nchw_cl, rois, P, scales, sr, mode="route", out=o))
+            ms, best = timeit(lambda: nb.roi_align_levels(nchw_cl, rois, P, scales, sr, mode="route", out=o, impl=a.impl))
             rec(f"roi_align_{P}x{P}_sr{sr}_{dist}", ms, best, K * C * P * P * 4 + inb + K * 20, K=K)
             del o
     if want("sum"):
         rois = synth.proposals(B, 1000, "nuclei").to(dev)
         f64 = [f.to(dev) for f in synth.fpn_levels(B, 64)][:2]
-        n64 = [nb.to_nhwc(f, cache=False).permute(0, 3, 1, 2) for f in f64]
+        n64 = nb.stage_levels(f64) if a.impl == "auto" else [nb.to_nhwc(f).permute(0, 3, 1, 2) for f in f64]
         o = torch.empty(rois.shape[0], 64, 7, 7, device=dev)
-        ms, best = timeit(lambda: nb.roi_align_levels(n64, rois, 7, [1 / 4, 1 / 8], 2, mode="sum", out=o))
+        ms, best = timeit(lambda: nb.roi_align_levels(n64, rois, 7, [1 / 4, 1 / 8], 2, mode="sum", out=o, impl=a.impl))
         rec("roi_align_7x7_sr2_sum01_C64", ms, best, o.numel() * 4 + sum(f.numel() * 4 for f in f64) + rois.shape[0] * 20)
     if want("nhwc"):
-        ms, best = timeit(lambda: [nb.to_nhwc(f, cache=False) for f in feats])
+        ms, best = timeit(lambda: [nb.to_nhwc(f) for f in feats])
         rec("nchw_to_nhwc_4levels", ms, best, 2 * sum(f.numel() * 4 for f in feats))
+        ms, best = timeit(lambda: [nb.to_cg32(f) for f in feats])
+        rec("nchw_to_cg32_4levels", ms, best, 2 * sum(f.numel() * 4 for f in feats))
     boxes, probs, scores = synth.nuclei_masks(8000, seed=0)
     boxes, probs, scores = boxes.to(dev), probs.to(dev), scores.to(dev)
     if want("paste"):
