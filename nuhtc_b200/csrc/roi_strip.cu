@@ -34,44 +34,33 @@
 namespace {
 
 constexpr int kCG = 32;                               // channels per group: 32 floats = one 128-byte line per cell
-constexpr int kBW = 60;                               // cells per staged row (ring row = 7680 B)
+constexpr int kBW = 48;                               // cells per staged row (ring row = 6144 B)
 constexpr int kXH = 18;                               // widest window staged on a level that needs several strips
-constexpr int kCore = kBW - kXH + 1;                  // 43: strip s owns window origins [s*kCore, (s+1)*kCore)
+constexpr int kCore = kBW - kXH + 1;                  // 31: strip s owns window origins [s*kCore, (s+1)*kCore)
 constexpr int kRMax = 18;                             // tallest staged window
 constexpr int kNU = 4;                                // unit descriptors in flight
 constexpr int kRowFloats = kBW * kCG;
 constexpr int kSmemMax = 232448;                      // 227 KB opt-in shared memory per CTA
 
-template <int P> struct StripRec;
-template <int P>
-struct StripCfg {
-    static constexpr int NW = 15;                     // consumer warps (+ the producer warp = 512 threads, 128 registers each)
-    static constexpr int NTHREADS = 32 * (NW + 1);
-    static constexpr int REC_BYTES = 96 + 2 * P * kMaxTap * 4;
-    // ring rows: whatever the records, unit slots and barriers leave of the shared memory
-    static constexpr int NR_RAW = (kSmemMax - NW * 2 * REC_BYTES - 1024 - 16 * NW) / (kRowFloats * 4 + 16);
-    static constexpr int NR = NR_RAW > 30 ? 30 : NR_RAW;
-    static_assert(NR >= kRMax + 2, "the ring must hold the tallest window plus some slack");
-};
-
-// One record per staged RoI, written by the prepass at the RoI's sorted position and fetched with one bulk copy:
-// the per-bin tap tables of both axes in the reference's fp32 op order.  The consumers work BIN-MAJOR and y-first:
-// for output row i they sweep only the ny[i] window rows that bin reaches (u[j] += wy * V[row][xs + j]) and then close
-// the bin with the x taps (out = sum_j wx[j] * u[j]).  Everything is statically indexed and both passes are sparse:
-// 2*NX*(ny + 1) packed FMAs per bin instead of the row-major form's 2*NX + 2*P per row, which spent two thirds of its
-// FMAs on zero weights (profiles/r02_roialign_strip.md).
+// One record per staged RoI, written by the prepass at the RoI's sorted position and fetched with one bulk copy: the x tap
+// tables and the dense per-row y weights in the reference's fp32 op order ("staging of sampling coordinates").
+// The consumers sweep the window rows once (x taps first), and the y pass is sparse at the granularity of groups of four
+// output rows: gs[g] / ge[g] bound the window rows that reach group g (bins 4g .. 4g+3), which cuts the sweep into counted
+// loops whose bodies only touch the accumulators of one group or of two neighbouring groups.
 template <int P>
 struct __align__(16) StripRec {
+    static constexpr int WYS = (P + 3) / 4 * 4;
     int k, y0, hh, x0;
     unsigned char xs[16];   // per output column: first x tap - x0
     signed char nx[16];     // per output column: x taps (0: no valid sample)
-    unsigned char ys[16];   // per output row: first y tap - y0
-    signed char ny[16];     // per output row: y taps (0: no valid sample)
-    int pad[4];
+    unsigned char gs[4], ge[4];   // per bin group: first / one-past-last window row that reaches it
+    unsigned char sB, eA;         // 7x7 shorthand: gs[1], ge[0]
+    unsigned char gdense, nxmax;  // a row reaches three groups: sweep every row into every bin; max x taps of a column
+    int pad[1];
     float wx[P][kMaxTap];
-    float wy[P][kMaxTap];   // already divided by the sample count
+    float wyd[kRMax][WYS];  // [window row][bin]: y weight / sample count, 0 where the bin misses the row
 };
-static_assert(sizeof(StripRec<7>) == StripCfg<7>::REC_BYTES && sizeof(StripRec<14>) == StripCfg<14>::REC_BYTES, "record size");
+static_assert(sizeof(StripRec<7>) == 64 + 7 * 32 + kRMax * 32 && sizeof(StripRec<14>) == 64 + 14 * 32 + kRMax * 64, "record layout");
 
 struct StripLevel {
     const float *data;
@@ -310,18 +299,64 @@ __global__ void __launch_bounds__(256) strip_records_kernel(StripArgs a) {
         rec->xs[lane] = (unsigned char)((lane < P && n > 0) ? first - g.x0 : 0);
         rec->nx[lane] = (signed char)(lane < P ? n : 0);
     }
+    int nxmax = lane < P ? n : 0;
+#pragma unroll
+    for (int o = 8; o; o >>= 1) nxmax = max(nxmax, __shfl_xor_sync(0xffffffffu, nxmax, o));
+    nxmax = __shfl_sync(0xffffffffu, nxmax, 0);
     if (lane < P) {
         *reinterpret_cast<float4 *>(&rec->wx[lane][0]) = make_float4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<float4 *>(&rec->wx[lane][4]) = make_float4(w[4], w[5], w[6], w[7]);
     }
-    if (lane >= 16 && lane < 32) {
+    // dense y weights: wyd[r][p] = w_p[y0 + r - first_p] where bin p reaches window row r, else 0
+    constexpr int WYS = StripRec<P>::WYS;
+    for (int e = lane; e < g.hh * WYS; e += 32) (&rec->wyd[0][0])[e] = 0.f;
+    __syncwarp();
+    const bool ybin = lane >= 16 && lane < 16 + P;
+    if (ybin) {
         const int p = lane - 16;
-        rec->ys[p] = (unsigned char)((p < P && n > 0) ? first - g.y0 : 0);
-        rec->ny[p] = (signed char)(p < P ? n : 0);
-        if (p < P) {
-            *reinterpret_cast<float4 *>(&rec->wy[p][0]) = make_float4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<float4 *>(&rec->wy[p][4]) = make_float4(w[4], w[5], w[6], w[7]);
+        for (int r = 0; r < g.hh; ++r) {
+            const int jj = g.y0 + r - first;
+            if ((unsigned)jj < (unsigned)n) {
+                float v = 0.f;
+#pragma unroll
+                for (int j = 0; j < kMaxTap; ++j)
+                    if (j == jj) v = w[j];
+                rec->wyd[r][p] = v;
+            }
         }
+    }
+    // bin groups: rows [gs, ge) reach group g = bins 4g .. 4g+3
+    int gs[4], ge[4];
+    bool dense = false;
+#pragma unroll
+    for (int gI = 0; gI < 4; ++gI) {
+        const bool in = ybin && n > 0 && (lane - 16) / 4 == gI;
+        int lo = in ? first - g.y0 : 255, hi = in ? first + n - g.y0 : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (hi <= lo) {   // no bin of the group has a valid sample: an empty stretch at the end of the previous group
+            lo = gI ? ge[gI - 1] : 0;
+            hi = lo;
+        }
+        if (gI && lo < gs[gI - 1]) lo = gs[gI - 1];   // the row ranges of the bins ascend; keep the bounds monotone
+        if (gI && hi < ge[gI - 1]) hi = ge[gI - 1];
+        gs[gI] = lo;
+        ge[gI] = hi;
+        if (gI >= 2 && gs[gI] < ge[gI - 2]) dense = true;   // a row reaches three groups
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int gI = 0; gI < 4; ++gI) {
+            rec->gs[gI] = (unsigned char)gs[gI];
+            rec->ge[gI] = (unsigned char)ge[gI];
+        }
+        rec->sB = (unsigned char)gs[1];
+        rec->eA = (unsigned char)ge[0];
+        rec->gdense = dense ? 1 : 0;
+        rec->nxmax = (unsigned char)nxmax;
     }
 }
 
@@ -332,134 +367,161 @@ struct __align__(16) UnitSlot {
     StripUnit u;
     int cg;        // channel group
     int row_base;  // position of row Y0 in the ring's running row count
-    int next_item; // shared pop counter of the consumer warps
+    int next_item; // shared pop counter of the consumers
     int valid;     // 0: no more units
 };
 
-// Consumer = ONE WARP per work item, no barrier between warps anywhere: lane = (channel-quad column q < 4, output column
-// pw < 7), 28 active lanes; an item is (RoI, group of 7 output columns) -- P = 14 has two column groups per RoI.  A lane
+// ---- pieces shared by the two strip kernels ---------------------------------------------------------------------------
+struct StripBars {
+    uint32_t full0, empty0, ufull0, uempty0, rfull0;
+};
+
+template <int NR>
+__device__ __forceinline__ void strip_producer(const StripArgs &a, UnitSlot *s_unit, float *s_ring, const StripBars &B) {
+    const int ncg = a.C / kCG;
+    const int nunits = a.counters[0] * ncg;
+    unsigned g = 0;   // running row count of this CTA's ring
+    for (unsigned uc = 0;; ++uc) {
+        const unsigned us = uc % kNU;
+        mbar_wait(B.uempty0 + 8 * us, ((uc / kNU) & 1) ^ 1);
+        const int u = atomicAdd(a.counters + 1, 1);
+        UnitSlot &S = s_unit[us];
+        if (u >= nunits) {
+            S.valid = 0;
+            mbar_arrive(B.ufull0 + 8 * us);
+            break;
+        }
+        const StripUnit d = a.units[u / ncg];
+        S.u = d;
+        S.cg = u % ncg;
+        S.row_base = (int)g;
+        S.next_item = 0;
+        S.valid = 1;
+        mbar_arrive(B.ufull0 + 8 * us);   // release: the slot's contents are visible to whoever acquires the phase
+        const StripLevel &lv = a.lv[d.level];
+        const float *src = lv.data + ((((size_t)d.b * ncg + S.cg) * lv.H + d.Y0) * lv.W + d.X0) * kCG;
+        const uint32_t bytes = (uint32_t)d.BW * kCG * 4;
+        const size_t rstride = (size_t)lv.W * kCG;
+        for (int y = d.Y0; y < d.Y1; ++y, ++g, src += rstride) {
+            const unsigned slot = g % NR;
+            mbar_wait(B.empty0 + 8 * slot, ((g / NR) & 1) ^ 1);
+            mbar_arrive_expect_tx(B.full0 + 8 * slot, bytes);
+            tma_bulk_g2s(smem_u32(s_ring + (size_t)slot * kRowFloats), src, bytes, B.full0 + 8 * slot);
+        }
+    }
+}
+
+// Rows [from, to) of the current unit are behind this consumer: one arrival per row on its slot's `empty` barrier (by the
+// consumer's warp 0 when `arrive`).  A slot's barrier only moves on to its next use once ALL consumers have arrived, and
+// the producer refills the slot only then -- so before arriving for a row the lane first sees that row's `full` phase
+// complete: that proves the slot's previous use has been released by everybody and this arrival is counted for the right
+// phase (a consumer that skips more than NR rows would otherwise arrive twice in one phase).  EVERY warp walks the skipped
+// rows' `full` phases: a parity wait can tell the current phase from the next one but not from the one after, so a warp
+// must have seen row g - NR land before it may wait for row g -- otherwise the wait passes at once and the warp reads a
+// slot that was never filled.  16 rows at a time: distinct slots per round.
+template <int NR>
+__device__ __forceinline__ void strip_release_rows(int from, int to, int row_base, int Y0, int lane, bool arrive, const StripBars &B) {
+    for (int base = from; base < to; base += 16) {
+        const int r = base + (lane & 15);
+        if (lane < 16 && r < to) {
+            const unsigned gg = (unsigned)(row_base + r - Y0);
+            mbar_wait(B.full0 + 8 * (gg % NR), (gg / NR) & 1);
+            if (arrive) mbar_arrive(B.empty0 + 8 * (gg % NR));
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 7x7: one warp per (RoI, channel group)
+// ---------------------------------------------------------------------------------------------
+// lane = (channel-quad column q < 4, output column pw < 7), 28 active lanes, no barrier between warps anywhere.  A lane
 // owns two float4 slices of the 32 channels (channels 4q.. and 16+4q..).  LDS.128 is served a quarter-warp at a time (8
 // lanes = 2 output columns x 4 quads): lanes of an odd column load their HIGH slice first, so the two columns of a phase
 // cover banks 0-15 and 16-31 and every tap load is conflict-free although the two columns read different cells.
-// The bin loop is a real loop (tiny code, ~60 registers): each bin's 8 results per lane go straight to global memory
-// (7 lanes of one channel write 28 contiguous bytes; L2 merges the partial sectors before they reach DRAM).
-template <int P>
-__global__ void __launch_bounds__(StripCfg<P>::NTHREADS, 1) roi_align_strip_kernel(const __grid_constant__ StripArgs a) {
-    using Cfg = StripCfg<P>;
-    using Rec = StripRec<P>;
-    constexpr int PP = P * P, NW = Cfg::NW, NR = Cfg::NR, GROUPS = P / 7;
+// Row-major, x first: t = sum_j wx[j] * V[row][xs + j], then the row feeds the output rows it reaches.  The y pass is
+// sparse at the granularity of two bin groups (bins 0-3, bins 4-6): the window rows split into a stretch that feeds only
+// the first group, a stretch that feeds both and a stretch that feeds only the second -- three counted loops with
+// statically named accumulators, no per-row control flow.
+struct Strip7Cfg {
+    static constexpr int NW = 15;                     // consumer warps (+ the producer warp = 512 threads, 128 registers each)
+    static constexpr int NTHREADS = 32 * (NW + 1);
+    static constexpr int TILE_FLOATS = 16 * 49;       // one 16-channel slice of a RoI: 3136 B, contiguous in the output
+    static constexpr int FIXED = NW * (TILE_FLOATS * 4 + 2 * (int)sizeof(StripRec<7>)) + kNU * (int)sizeof(UnitSlot) + 16 * NW + 16 * kNU + 256;
+    static constexpr int NR_RAW = (kSmemMax - FIXED) / (kRowFloats * 4 + 16);
+    static constexpr int NR = NR_RAW > 32 ? 32 : NR_RAW;
+    static_assert(NR >= kRMax + 2, "the ring must hold the tallest window plus some slack");
+};
+
+__global__ void __launch_bounds__(Strip7Cfg::NTHREADS, 1) roi_align_strip7_kernel(const __grid_constant__ StripArgs a) {
+    using Cfg = Strip7Cfg;
+    using Rec = StripRec<7>;
+    constexpr int P = 7, PP = 49, NW = Cfg::NW, NR = Cfg::NR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_ring = reinterpret_cast<float *>(smem_raw);                              // [NR][kBW][32]
-    Rec *s_rec = reinterpret_cast<Rec *>(s_ring + (size_t)NR * kRowFloats);           // [NW][2]
+    float *s_tile = s_ring + (size_t)NR * kRowFloats;                                 // [NW][TILE_FLOATS]
+    Rec *s_rec = reinterpret_cast<Rec *>(s_tile + NW * Cfg::TILE_FLOATS);            // [NW][2]
     UnitSlot *s_unit = reinterpret_cast<UnitSlot *>(s_rec + NW * 2);                  // [kNU]
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_unit + kNU);                     // full[NR], empty[NR], ufull[kNU], uempty[kNU], rfull[NW*2]
-    const uint32_t full0 = smem_u32(s_bar), empty0 = full0 + 8 * NR, ufull0 = empty0 + 8 * NR, uempty0 = ufull0 + 8 * kNU,
-                   rfull0 = uempty0 + 8 * kNU;
+    StripBars B;
+    B.full0 = smem_u32(s_bar);
+    B.empty0 = B.full0 + 8 * NR;
+    B.ufull0 = B.empty0 + 8 * NR;
+    B.uempty0 = B.ufull0 + 8 * kNU;
+    B.rfull0 = B.uempty0 + 8 * kNU;
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < NR; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, NW);
+            mbar_init(B.full0 + 8 * s, 1);
+            mbar_init(B.empty0 + 8 * s, NW);
         }
         for (int s = 0; s < kNU; ++s) {
-            mbar_init(ufull0 + 8 * s, 1);
-            mbar_init(uempty0 + 8 * s, NW);
+            mbar_init(B.ufull0 + 8 * s, 1);
+            mbar_init(B.uempty0 + 8 * s, NW);
         }
-        for (int s = 0; s < NW * 2; ++s) mbar_init(rfull0 + 8 * s, 1);
+        for (int s = 0; s < NW * 2; ++s) mbar_init(B.rfull0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int ncg = a.C / kCG;
-
     if (tid < 32) {
-        // =========================== producer warp: unit scheduler + row streamer ===========================
-        if (tid != 0) return;
-        const int nunits = a.counters[0] * ncg;
-        unsigned g = 0;   // running row count of this CTA's ring
-        for (unsigned uc = 0;; ++uc) {
-            const unsigned us = uc % kNU;
-            mbar_wait(uempty0 + 8 * us, ((uc / kNU) & 1) ^ 1);
-            const int u = atomicAdd(a.counters + 1, 1);
-            UnitSlot &S = s_unit[us];
-            if (u >= nunits) {
-                S.valid = 0;
-                mbar_arrive(ufull0 + 8 * us);
-                break;
-            }
-            const StripUnit d = a.units[u / ncg];
-            S.u = d;
-            S.cg = u % ncg;
-            S.row_base = (int)g;
-            S.next_item = 0;
-            S.valid = 1;
-            mbar_arrive(ufull0 + 8 * us);   // release: the slot's contents are visible to the warps that acquire the phase
-            const StripLevel &lv = a.lv[d.level];
-            const float *src = lv.data + ((((size_t)d.b * ncg + S.cg) * lv.H + d.Y0) * lv.W + d.X0) * kCG;
-            const uint32_t bytes = (uint32_t)d.BW * kCG * 4;
-            const size_t rstride = (size_t)lv.W * kCG;
-            for (int y = d.Y0; y < d.Y1; ++y, ++g, src += rstride) {
-                const unsigned slot = g % NR;
-                mbar_wait(empty0 + 8 * slot, ((g / NR) & 1) ^ 1);
-                mbar_arrive_expect_tx(full0 + 8 * slot, bytes);
-                tma_bulk_g2s(smem_u32(s_ring + (size_t)slot * kRowFloats), src, bytes, full0 + 8 * slot);
-            }
-        }
+        if (tid == 0) strip_producer<NR>(a, s_unit, s_ring, B);
         return;
     }
-
-    // =========================== consumer warps ===========================
     const int cw = (tid >> 5) - 1, lane = tid & 31;
     const bool worker = lane < 28;
-    const int q = lane & 3, pwl = worker ? lane >> 2 : 0;   // output column inside the item's column group
-    const bool odd = (pwl & 1) != 0;                        // this lane keeps its HIGH slice in register set 0
+    const int q = lane & 3, pw = worker ? lane >> 2 : 0;
+    const bool odd = (pw & 1) != 0;   // this lane keeps its HIGH slice in register set 0
+    float *tile = s_tile + cw * Cfg::TILE_FLOATS;
     Rec *recs = s_rec + cw * 2;
-    const uint32_t rf0 = rfull0 + 8 * (cw * 2);
+    const uint32_t rf0 = B.rfull0 + 8 * (cw * 2);
     unsigned rec_uses[2] = {0u, 0u};
-    // Rows [from, to) of the current unit are behind this warp: one arrival per row on its slot's `empty` barrier.  A
-    // slot's barrier only moves on to its next use once ALL warps have arrived, and the producer refills the slot only
-    // then -- so before arriving for a row the lane first sees that row's `full` phase complete: that proves the slot's
-    // previous use has been released by everybody and this arrival is counted for the right phase (a warp that skips more
-    // than NR rows would otherwise arrive twice in one phase; and a parity wait can tell the current phase from the next
-    // one but not from the one after, so the warp must have seen row g - NR land before it may wait for row g).
-    // 16 rows at a time: distinct slots per round.
-    auto release_rows = [&](int from, int to, int row_base, int Y0) {
-        for (int base = from; base < to; base += 16) {
-            const int r = base + (lane & 15);
-            if (lane < 16 && r < to) {
-                const unsigned gg = (unsigned)(row_base + r - Y0);
-                mbar_wait(full0 + 8 * (gg % NR), (gg / NR) & 1);
-                mbar_arrive(empty0 + 8 * (gg % NR));
-            }
-            __syncwarp();
-        }
-    };
+    bool store_pending = false;
 
     for (unsigned uc = 0;; ++uc) {
         const unsigned us = uc % kNU;
-        mbar_wait(ufull0 + 8 * us, (uc / kNU) & 1);
+        mbar_wait(B.ufull0 + 8 * us, (uc / kNU) & 1);
         UnitSlot &S = s_unit[us];
         if (!S.valid) break;
         const StripUnit d = S.u;
         const int cg = S.cg, row_base = S.row_base;
-        const int nitems = d.item_count * GROUPS;
         const Rec *gtab = reinterpret_cast<const Rec *>(a.records) + d.item_begin;
         int passed = d.Y0;   // first row of this unit the warp has not released yet
         auto fetch = [&](int item, int buf) {   // lane 0 only: the whole fixed-size record with one bulk copy
             mbar_arrive_expect_tx(rf0 + 8 * buf, (uint32_t)sizeof(Rec));
-            tma_bulk_g2s(smem_u32(&recs[buf]), gtab + item / GROUPS, (uint32_t)sizeof(Rec), rf0 + 8 * buf);
+            tma_bulk_g2s(smem_u32(&recs[buf]), gtab + item, (uint32_t)sizeof(Rec), rf0 + 8 * buf);
         };
         int cur = 0, curbuf = 0;
         if (lane == 0) {
             cur = atomicAdd(&S.next_item, 1);
-            if (cur < nitems) fetch(cur, 0);
+            if (cur < d.item_count) fetch(cur, 0);
         }
         cur = __shfl_sync(0xffffffffu, cur, 0);
-        while (cur < nitems) {
+        while (cur < d.item_count) {
             // ---- next item: pop + prefetch its record into the other buffer
             int nxt = 0;
             if (lane == 0) {
                 nxt = atomicAdd(&S.next_item, 1);
-                if (nxt < nitems) fetch(nxt, curbuf ^ 1);
+                if (nxt < d.item_count) fetch(nxt, curbuf ^ 1);
             }
             nxt = __shfl_sync(0xffffffffu, nxt, 0);
             // ---- this item's record
@@ -467,132 +529,408 @@ __global__ void __launch_bounds__(StripCfg<P>::NTHREADS, 1) roi_align_strip_kern
             ++rec_uses[curbuf];
             const Rec &R = recs[curbuf];
             const int k = R.k, y0 = R.y0, hh = R.hh;
-            const int pw = pwl + 7 * (cur % GROUPS);
-            // ---- release the rows above this window, then wait for the window's rows
-            release_rows(passed, y0, row_base, d.Y0);
-            passed = max(passed, y0);
-            {
-                const unsigned gg = (unsigned)(row_base + y0 - d.Y0) + (lane < hh ? lane : 0);
-                mbar_wait(full0 + 8 * (gg % NR), (gg / NR) & 1);
-                __syncwarp();
+            // ---- release the rows above this window
+            strip_release_rows<NR>(passed, y0, row_base, d.Y0, lane, true, B);
+            const unsigned pos0 = (unsigned)(row_base + y0 - d.Y0);   // ring position of the window's first row
+            // The window's rows are waited for four at a time while the sweep advances, and released as soon as neither
+            // this item nor the warp's NEXT item (whose window top is read from its record once that has landed) needs
+            // them: a warp then holds a few rows instead of its whole window for the whole item, which is what lets the
+            // producer run ahead (with whole-window holds the 15 warps pinned spread + window = the entire ring and every
+            // row load was exposed latency: 65 M spins on `full` barriers, profiles/r02_roialign_strip.md).
+            const int nxu = R.nxmax;             // warp-uniform tap count: columns with fewer taps pad with weight 0
+            const bool single = nxu <= 4 && !(a.dbg & 4);   // one sweep only: rows can be released behind it
+            int rel = 0;                         // rows [0, rel) of the window are released
+            int hold = 0;                        // rows < hold may be released once swept
+            bool hold_known = false;
+            if (nxt >= d.item_count) {
+                hold = hh;
+                hold_known = true;
             }
-            // ---- separable pooling out of the ring, bin-major and y-first (see StripRec)
-            if (worker && !(a.dbg & 1)) {
-                const int nx = R.nx[pw];
-                const int xoff = R.x0 - d.X0 + (int)R.xs[pw];
+            float2 acc[2][P][2];   // [register set][output row][channel pair]
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int i = 0; i < P; ++i) acc[s][i][0] = acc[s][i][1] = make_float2(0.f, 0.f);
+            if (nxu > 0 && !(a.dbg & 1)) {
+                const int nx = worker ? (int)R.nx[pw] : 0;
+                const int xoff = R.x0 - d.X0 + (worker ? (int)R.xs[pw] : 0);
                 const float *wxp = R.wx[pw];
-                const unsigned slot = (unsigned)(row_base + y0 - d.Y0) % NR;
                 // register set 0 reads this float offset inside a cell, set 1 the other half of the 128-byte line
                 const float *colp = s_ring + (size_t)xoff * kCG + (odd ? 16 : 0) + 4 * q;
                 const int d1 = odd ? -16 : 16;
-                // channel of set s, element 0: 16 * (s ^ odd) + 4q
-                float *out0 = a.out + ((size_t)k * a.C + (size_t)cg * kCG + (odd ? 16 : 0) + 4 * q) * PP + pw;
-                const int o1 = d1 * PP;
-                float4 bz0 = make_float4(0.f, 0.f, 0.f, 0.f), bz1 = bz0;
-                if (a.bias) {
-                    const float *bp = a.bias + (size_t)k * a.C + cg * kCG + (odd ? 16 : 0) + 4 * q;
-                    bz0 = ldg_f4(bp);
-                    bz1 = ldg_f4(bp + d1);
-                }
-                auto bins = [&](auto NXC, int j0, bool first_pass) {   // x taps j0 .. j0 + NX - 1 of this lane's column
-                    constexpr int NX = decltype(NXC)::value;
-                    constexpr int NXR = NX > 0 ? NX : 1;
-                    float wx[NXR];
+                const int sB = R.sB, eA = R.eA;   // rows [sB, hh) feed bins 4-6, rows [0, eA) feed bins 0-3
+                // GRP 1: bins 0-3, 2: bins 4-6, 3: all.  NX is the warp's tap count; a lane with fewer taps repeats its
+                // last cell with weight 0 (a cell of its own bin: a padded tap never touches memory the lane does not own)
+                auto rows = [&](auto NXC, auto GRPC, int j0, int r0, int r1) {
+                    constexpr int NX = decltype(NXC)::value, GRP = decltype(GRPC)::value;
+                    float wx[NX];
+                    int toff[NX];
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) wx[j] = wxp[j0 + j];
+                    for (int j = 0; j < NX; ++j) {
+                        const bool ok = j0 + j < nx;
+                        wx[j] = ok ? wxp[j0 + j] : 0.f;
+                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG;
+                    }
 #pragma unroll 1
-                    for (int i = 0; i < P; ++i) {
-                        const int nyi = R.ny[i];                      // uniform over the warp
-                        unsigned sl = slot + R.ys[i];
-                        if (sl >= NR) sl -= NR;
-                        float2 u[2][NXR][2];
-#pragma unroll
-                        for (int s = 0; s < 2; ++s)
-#pragma unroll
-                            for (int j = 0; j < NXR; ++j) u[s][j][0] = u[s][j][1] = make_float2(0.f, 0.f);
+                    for (int rc = r0; rc < r1; rc += 4) {
+                        const int nrow = min(4, r1 - rc);
+                        if (lane < nrow) {
+                            const unsigned gg = pos0 + rc + lane;
+                            mbar_wait(B.full0 + 8 * (gg % NR), (gg / NR) & 1);
+                        }
+                        __syncwarp();
+                        unsigned sl = (pos0 + rc) % NR;
 #pragma unroll 1
-                        for (int jj = 0; jj < nyi; ++jj) {
-                            const float w = R.wy[i][jj];
-                            const float *row = colp + (size_t)sl * kRowFloats + j0 * kCG;
-                            float4 v[2][NXR];
+                        for (int r = rc; r < rc + nrow; ++r) {
+                            const float *row = colp + (size_t)sl * kRowFloats;
+                            float4 v[2][NX];
 #pragma unroll
                             for (int s = 0; s < 2; ++s)
 #pragma unroll
-                                for (int j = 0; j < NX; ++j) v[s][j] = *reinterpret_cast<const float4 *>(row + j * kCG + s * d1);
+                                for (int j = 0; j < NX; ++j) v[s][j] = *reinterpret_cast<const float4 *>(row + toff[j] + s * d1);
+                            const float4 wa = *reinterpret_cast<const float4 *>(&R.wyd[r][0]);
+                            const float4 wb = *reinterpret_cast<const float4 *>(&R.wyd[r][4]);
+                            float2 t[2][2];
 #pragma unroll
-                            for (int s = 0; s < 2; ++s)
+                            for (int s = 0; s < 2; ++s) {
+                                t[s][0] = t[s][1] = make_float2(0.f, 0.f);
 #pragma unroll
                                 for (int j = 0; j < NX; ++j) {
-                                    u[s][j][0] = ffma2(w, make_float2(v[s][j].x, v[s][j].y), u[s][j][0]);
-                                    u[s][j][1] = ffma2(w, make_float2(v[s][j].z, v[s][j].w), u[s][j][1]);
+                                    t[s][0] = ffma2(wx[j], make_float2(v[s][j].x, v[s][j].y), t[s][0]);
+                                    t[s][1] = ffma2(wx[j], make_float2(v[s][j].z, v[s][j].w), t[s][1]);
+                                }
+                            }
+#pragma unroll
+                            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    if (GRP & 1) {
+                                        acc[s][0][h] = ffma2(wa.x, t[s][h], acc[s][0][h]);
+                                        acc[s][1][h] = ffma2(wa.y, t[s][h], acc[s][1][h]);
+                                        acc[s][2][h] = ffma2(wa.z, t[s][h], acc[s][2][h]);
+                                        acc[s][3][h] = ffma2(wa.w, t[s][h], acc[s][3][h]);
+                                    }
+                                    if (GRP & 2) {
+                                        acc[s][4][h] = ffma2(wb.x, t[s][h], acc[s][4][h]);
+                                        acc[s][5][h] = ffma2(wb.y, t[s][h], acc[s][5][h]);
+                                        acc[s][6][h] = ffma2(wb.z, t[s][h], acc[s][6][h]);
+                                    }
                                 }
                             if (++sl == NR) sl = 0;
                         }
-                        float2 r[2][2];
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            r[s][0] = r[s][1] = make_float2(0.f, 0.f);
-#pragma unroll
-                            for (int j = 0; j < NX; ++j) {
-                                r[s][0] = ffma2(wx[j], u[s][j][0], r[s][0]);
-                                r[s][1] = ffma2(wx[j], u[s][j][1], r[s][1]);
+                        // ---- rows behind the sweep go back to the producer
+                        if (single && rc == rel) {   // the swept stretch is contiguous with what is already released
+                            if (!hold_known) {
+                                // ONE lane probes the next record's barrier and reads its window top; the warp takes that
+                                // lane's answer (32 separate probes can straddle the phase flip and disagree, and a warp
+                                // that disagrees about `rel` falls apart at the next __syncwarp)
+                                int h = -1;
+                                if (lane == 0 && mbar_test(rf0 + 8 * (curbuf ^ 1), rec_uses[curbuf ^ 1] & 1)) h = recs[curbuf ^ 1].y0 - y0;
+                                h = __shfl_sync(0xffffffffu, h, 0);
+                                if (h >= 0) {
+                                    hold = h;
+                                    hold_known = true;
+                                }
+                            }
+                            const int lim = min(rc + nrow, hold);
+                            __syncwarp();   // every lane has read the rows
+                            if (lim > rel) {
+                                if (lane < lim - rel) mbar_arrive(B.empty0 + 8 * ((pos0 + rel + lane) % NR));
+                                rel = lim;
                             }
                         }
-                        float *op = out0 + i * P;
-                        if (a.dbg & 2) {
-                            if (r[0][0].x + r[0][0].y + r[0][1].x + r[0][1].y + r[1][0].x + r[1][0].y + r[1][1].x + r[1][1].y == 12345.678f) op[0] = 1.f;
-                        } else if (first_pass) {
-                            __stcs(op, r[0][0].x + bz0.x);
-                            __stcs(op + PP, r[0][0].y + bz0.y);
-                            __stcs(op + 2 * PP, r[0][1].x + bz0.z);
-                            __stcs(op + 3 * PP, r[0][1].y + bz0.w);
-                            __stcs(op + o1, r[1][0].x + bz1.x);
-                            __stcs(op + o1 + PP, r[1][0].y + bz1.y);
-                            __stcs(op + o1 + 2 * PP, r[1][1].x + bz1.z);
-                            __stcs(op + o1 + 3 * PP, r[1][1].y + bz1.w);
-                        } else {   // second pass of a bin wider than 4 taps: add to what the first pass stored
-                            op[0] += r[0][0].x;
-                            op[PP] += r[0][0].y;
-                            op[2 * PP] += r[0][1].x;
-                            op[3 * PP] += r[0][1].y;
-                            op[o1] += r[1][0].x;
-                            op[o1 + PP] += r[1][0].y;
-                            op[o1 + 2 * PP] += r[1][1].x;
-                            op[o1 + 3 * PP] += r[1][1].y;
-                        }
                     }
                 };
-                // exact tap counts only (no zero-weight padding: a padded tap would multiply whatever sits past the bin by
-                // 0, and 0 * inf is NaN); nx == 0 (no valid sample in this column) stores the bias / zeros; bins wider than
-                // 4 taps (large RoIs) take two passes of up to 4 taps, the second one read-modify-writes the lane's own
-                // stores (same thread, same addresses: program order)
-                auto taps = [&](int n, int j0, bool first_pass) {
-                    switch (n) {
-                        case 0: bins(std::integral_constant<int, 0>{}, j0, first_pass); break;
-                        case 1: bins(std::integral_constant<int, 1>{}, j0, first_pass); break;
-                        case 2: bins(std::integral_constant<int, 2>{}, j0, first_pass); break;
-                        case 3: bins(std::integral_constant<int, 3>{}, j0, first_pass); break;
-                        default: bins(std::integral_constant<int, 4>{}, j0, first_pass); break;
-                    }
+                auto sweep = [&](auto NXC, int j0) {
+                    const int a1 = min(sB, eA), b0 = max(sB, eA);
+                    rows(NXC, std::integral_constant<int, 1>{}, j0, 0, a1);
+                    rows(NXC, std::integral_constant<int, 3>{}, j0, sB, eA);   // empty unless sB < eA
+                    rows(NXC, std::integral_constant<int, 2>{}, j0, b0, hh);
                 };
-                taps(nx < 4 ? (nx < 0 ? 0 : nx) : 4, 0, true);
-                if (nx > 4) taps(nx - 4, 4, false);
+                // bins wider than 4 taps take further sweeps over taps 4.., 8.. (one call site: the sweep code exists once)
+#pragma unroll 1
+                for (int j0 = 0; j0 < nxu; j0 += 4) {
+                    switch (nxu - j0 < 4 ? nxu - j0 : 4) {
+                        case 1: sweep(std::integral_constant<int, 1>{}, j0); break;
+                        case 2: sweep(std::integral_constant<int, 2>{}, j0); break;
+                        case 3: sweep(std::integral_constant<int, 3>{}, j0); break;
+                        default: sweep(std::integral_constant<int, 4>{}, j0); break;
+                    }
+                }
             }
-            __syncwarp();   // every lane is done with the ring rows and the record before the warp moves on
+            passed = max(passed, y0 + rel);
+            // ---- flush: two 16-channel slices through the warp's tile, one asynchronous bulk store each
+            float *outp = a.out + ((size_t)k * a.C + (size_t)cg * kCG) * PP;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                if (lane == 0 && store_pending) tma_store_wait_read();   // the previous store has read the tile
+                __syncwarp();
+                if (worker && !(a.dbg & 2)) {
+                    const bool hi = odd != (f == 1);   // slice f sits in register set f ^ odd
+                    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a.bias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 16 * f + 4 * q);
+                    float *tp = tile + (4 * q) * PP + pw;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        float a0 = hi ? acc[1][i][0].x : acc[0][i][0].x, a1 = hi ? acc[1][i][0].y : acc[0][i][0].y;
+                        float a2 = hi ? acc[1][i][1].x : acc[0][i][1].x, a3 = hi ? acc[1][i][1].y : acc[0][i][1].y;
+                        if (a.bias) {
+                            a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
+                        }
+                        tp[i * P] = a0;
+                        tp[i * P + PP] = a1;
+                        tp[i * P + 2 * PP] = a2;
+                        tp[i * P + 3 * PP] = a3;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_bulk_s2g(outp + (size_t)f * Cfg::TILE_FLOATS, smem_u32(tile), Cfg::TILE_FLOATS * 4);
+                    store_pending = true;
+                }
+            }
             cur = nxt;
             curbuf ^= 1;
         }
         // ---- unit done for this warp: release its remaining rows and the unit slot
-        release_rows(passed, d.Y1, row_base, d.Y0);
-        if (lane == 0) mbar_arrive(uempty0 + 8 * us);
+        strip_release_rows<NR>(passed, d.Y1, row_base, d.Y0, lane, true, B);
+        if (lane == 0) mbar_arrive(B.uempty0 + 8 * us);
     }
+    if (lane == 0 && store_pending) tma_store_wait_all();
 }
 
-template <int P>
-size_t strip_smem_bytes() {
-    using Cfg = StripCfg<P>;
-    return (size_t)Cfg::NR * kRowFloats * 4 + (size_t)Cfg::NW * 2 * sizeof(StripRec<P>) + kNU * sizeof(UnitSlot) +
-           8 * (2 * Cfg::NR + 2 * kNU + 2 * Cfg::NW) + 128;
+static size_t strip7_smem_bytes() {
+    return (size_t)Strip7Cfg::NR * kRowFloats * 4 + Strip7Cfg::FIXED + 16 * Strip7Cfg::NR;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 14x14: a team of 4 warps per (RoI, channel group)
+// ---------------------------------------------------------------------------------------------
+// thread = (channel quad q < 8, output column pw < 14): 112 threads, 4 channels each; a quarter-warp reads the 8 quads of
+// ONE cell (128 contiguous bytes), so the tap loads are conflict-free.  Same row-major sweep as the 7x7 kernel with four
+// bin groups (0-3, 4-7, 8-11, 12-13): a row feeds one group or two neighbouring ones, which gives seven counted loops.
+// The [32][14][14] result leaves in two 16-channel phases through the team tile (12.5 KB), one bulk store each.
+struct Strip14Cfg {
+    static constexpr int NT = 3, TW = 4, TEAM = TW * 32;
+    static constexpr int NTHREADS = 32 + NT * TEAM;
+    static constexpr int TILE_FLOATS = 16 * 196;
+    static constexpr int FIXED = NT * (TILE_FLOATS * 4 + 2 * (int)sizeof(StripRec<14>)) + kNU * (int)sizeof(UnitSlot) + 64 * NT + 16 * kNU + 256;
+    static constexpr int NR_RAW = (kSmemMax - FIXED) / (kRowFloats * 4 + 16);
+    static constexpr int NR = NR_RAW > 32 ? 32 : NR_RAW;
+    static_assert(NR >= kRMax + 2, "the ring must hold the tallest window plus some slack");
+};
+
+__global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_kernel(const __grid_constant__ StripArgs a) {
+    using Cfg = Strip14Cfg;
+    using Rec = StripRec<14>;
+    constexpr int P = 14, PP = 196, NT = Cfg::NT, TEAM = Cfg::TEAM, NR = Cfg::NR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_ring = reinterpret_cast<float *>(smem_raw);                              // [NR][kBW][32]
+    float *s_tile = s_ring + (size_t)NR * kRowFloats;                                 // [NT][TILE_FLOATS]
+    Rec *s_rec = reinterpret_cast<Rec *>(s_tile + NT * Cfg::TILE_FLOATS);            // [NT][2]
+    UnitSlot *s_unit = reinterpret_cast<UnitSlot *>(s_rec + NT * 2);                  // [kNU]
+    int *s_pop = reinterpret_cast<int *>(s_unit + kNU);                               // [NT][2] broadcast of the popped item
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_pop + 8);                        // full[NR], empty[NR], ufull[kNU], uempty[kNU], rfull[NT*2]
+    StripBars B;
+    B.full0 = smem_u32(s_bar);
+    B.empty0 = B.full0 + 8 * NR;
+    B.ufull0 = B.empty0 + 8 * NR;
+    B.uempty0 = B.ufull0 + 8 * kNU;
+    B.rfull0 = B.uempty0 + 8 * kNU;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < NR; ++s) {
+            mbar_init(B.full0 + 8 * s, 1);
+            mbar_init(B.empty0 + 8 * s, NT);
+        }
+        for (int s = 0; s < kNU; ++s) {
+            mbar_init(B.ufull0 + 8 * s, 1);
+            mbar_init(B.uempty0 + 8 * s, NT);
+        }
+        for (int s = 0; s < NT * 2; ++s) mbar_init(B.rfull0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) strip_producer<NR>(a, s_unit, s_ring, B);
+        return;
+    }
+    const int ct = tid - 32;
+    const int team = ct / TEAM, tt = ct % TEAM, twarp = tt >> 5, lane = tt & 31;
+    const bool worker = tt < 8 * P;
+    const int q = tt & 7, pw = worker ? tt >> 3 : 0;
+    float *tile = s_tile + team * Cfg::TILE_FLOATS;
+    Rec *recs = s_rec + team * 2;
+    const uint32_t rf0 = B.rfull0 + 8 * (team * 2);
+    const int bar_id = 1 + team;
+    auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TEAM) : "memory"); };
+    // tile write: the four channels of a thread are written in an order rotated by q/2 (784*q = 16*q mod 32: without the
+    // rotation the quads of a phase would pile onto two bank groups)
+    const int rot = (q >> 1) & 3;
+    const bool r1 = rot & 1, r2 = rot & 2;
+    unsigned rec_uses[2] = {0u, 0u};
+    bool store_pending = false;
+
+    for (unsigned uc = 0;; ++uc) {
+        const unsigned us = uc % kNU;
+        mbar_wait(B.ufull0 + 8 * us, (uc / kNU) & 1);
+        UnitSlot &S = s_unit[us];
+        if (!S.valid) break;
+        const StripUnit d = S.u;
+        const int cg = S.cg, row_base = S.row_base;
+        const Rec *gtab = reinterpret_cast<const Rec *>(a.records) + d.item_begin;
+        int passed = d.Y0;
+        auto fetch = [&](int item, int buf) {   // tt == 0 only
+            mbar_arrive_expect_tx(rf0 + 8 * buf, (uint32_t)sizeof(Rec));
+            tma_bulk_g2s(smem_u32(&recs[buf]), gtab + item, (uint32_t)sizeof(Rec), rf0 + 8 * buf);
+        };
+        int cur = 0, curbuf = 0;
+        unsigned it = 0;   // s_pop is double buffered: the pop of iteration i+1 is written while iteration i's is still read
+        if (tt == 0) {
+            cur = atomicAdd(&S.next_item, 1);
+            s_pop[team * 2] = cur;
+            if (cur < d.item_count) fetch(cur, 0);
+        }
+        team_sync();
+        cur = s_pop[team * 2];
+        while (cur < d.item_count) {
+            if (tt == 0) {
+                const int nxt = atomicAdd(&S.next_item, 1);
+                s_pop[team * 2 + ((it + 1) & 1)] = nxt;
+                if (nxt < d.item_count) fetch(nxt, curbuf ^ 1);
+            }
+            mbar_wait(rf0 + 8 * curbuf, rec_uses[curbuf] & 1);
+            ++rec_uses[curbuf];
+            const Rec &R = recs[curbuf];
+            const int k = R.k, y0 = R.y0, hh = R.hh;
+            strip_release_rows<NR>(passed, y0, row_base, d.Y0, lane, twarp == 0, B);
+            passed = max(passed, y0);
+            {
+                const unsigned gg = (unsigned)(row_base + y0 - d.Y0) + (lane < hh ? lane : 0);
+                mbar_wait(B.full0 + 8 * (gg % NR), (gg / NR) & 1);
+                __syncwarp();
+            }
+            float2 acc[P][2];
+#pragma unroll
+            for (int i = 0; i < P; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+            const int nxu = R.nxmax;   // team-uniform tap count: columns with fewer taps pad with weight 0 (no divergence)
+            if (nxu > 0 && !(a.dbg & 1)) {
+                const int nx = worker ? (int)R.nx[pw] : 0;
+                const int xoff = R.x0 - d.X0 + (worker ? (int)R.xs[pw] : 0);
+                const float *wxp = R.wx[pw];
+                const unsigned slot0 = (unsigned)(row_base + y0 - d.Y0) % NR;
+                const float *colp = s_ring + (size_t)xoff * kCG + 4 * q;
+                // GRP bit g: bins 4g .. 4g+3
+                auto rows = [&](auto NXC, auto GRPC, int j0, int r0, int r1_) {
+                    constexpr int NX = decltype(NXC)::value, GRP = decltype(GRPC)::value;
+                    float wx[NX];
+                    int toff[NX];
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) {
+                        const bool ok = j0 + j < nx;
+                        wx[j] = ok ? wxp[j0 + j] : 0.f;
+                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG;   // a padded tap repeats the lane's own last cell
+                    }
+                    unsigned sl = slot0 + r0;
+                    if (sl >= NR) sl -= NR;
+#pragma unroll 1
+                    for (int r = r0; r < r1_; ++r) {
+                        const float *row = colp + (size_t)sl * kRowFloats;
+                        float4 v[NX];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) v[j] = *reinterpret_cast<const float4 *>(row + toff[j]);
+                        float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) {
+                            t0 = ffma2(wx[j], make_float2(v[j].x, v[j].y), t0);
+                            t1 = ffma2(wx[j], make_float2(v[j].z, v[j].w), t1);
+                        }
+#pragma unroll
+                        for (int gI = 0; gI < 4; ++gI) {
+                            if (GRP & (1 << gI)) {
+                                const float4 w = *reinterpret_cast<const float4 *>(&R.wyd[r][4 * gI]);
+                                const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (4 * gI + e < P) {
+                                        acc[(4 * gI + e) % P][0] = ffma2(ws[e], t0, acc[(4 * gI + e) % P][0]);
+                                        acc[(4 * gI + e) % P][1] = ffma2(ws[e], t1, acc[(4 * gI + e) % P][1]);
+                                    }
+                                }
+                            }
+                        }
+                        if (++sl == NR) sl = 0;
+                    }
+                };
+                auto sweep = [&](auto NXC, int j0) {
+                    if (R.gdense) {   // a row feeds three groups (very small RoIs): every row feeds every bin
+                        rows(NXC, std::integral_constant<int, 15>{}, j0, 0, hh);
+                        return;
+                    }
+                    const int s1 = R.gs[1], s2 = R.gs[2], s3 = R.gs[3], e0 = R.ge[0], e1 = R.ge[1], e2 = R.ge[2];
+                    rows(NXC, std::integral_constant<int, 1>{}, j0, 0, min(e0, s1));
+                    rows(NXC, std::integral_constant<int, 3>{}, j0, s1, e0);
+                    rows(NXC, std::integral_constant<int, 2>{}, j0, max(e0, s1), min(e1, s2));
+                    rows(NXC, std::integral_constant<int, 6>{}, j0, s2, e1);
+                    rows(NXC, std::integral_constant<int, 4>{}, j0, max(e1, s2), min(e2, s3));
+                    rows(NXC, std::integral_constant<int, 12>{}, j0, s3, e2);
+                    rows(NXC, std::integral_constant<int, 8>{}, j0, max(e2, s3), hh);
+                };
+#pragma unroll 1
+                for (int j0 = 0; j0 < nxu; j0 += 4) {   // one call site: the sweep code exists once
+                    switch (nxu - j0 < 4 ? nxu - j0 : 4) {
+                        case 1: sweep(std::integral_constant<int, 1>{}, j0); break;
+                        case 2: sweep(std::integral_constant<int, 2>{}, j0); break;
+                        case 3: sweep(std::integral_constant<int, 3>{}, j0); break;
+                        default: sweep(std::integral_constant<int, 4>{}, j0); break;
+                    }
+                }
+            }
+            // ---- flush: two 16-channel phases through the team tile
+            float *outp = a.out + ((size_t)k * a.C + (size_t)cg * kCG) * PP;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                if (tt == 0 && store_pending) tma_store_wait_read();
+                team_sync();
+                if (worker && (q >> 2) == f && !(a.dbg & 2)) {
+                    const int cl = 4 * (q & 3);
+                    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a.bias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 4 * q);
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        float a0 = acc[i][0].x, a1 = acc[i][0].y, a2 = acc[i][1].x, a3 = acc[i][1].y;
+                        if (a.bias) {
+                            a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
+                        }
+                        float *tp = tile + i * P + pw;
+                        const float b0 = r2 ? a2 : a0, b1 = r2 ? a3 : a1, b2 = r2 ? a0 : a2, b3 = r2 ? a1 : a3;
+                        tp[(cl + ((0 + rot) & 3)) * PP] = r1 ? b1 : b0;
+                        tp[(cl + ((1 + rot) & 3)) * PP] = r1 ? b2 : b1;
+                        tp[(cl + ((2 + rot) & 3)) * PP] = r1 ? b3 : b2;
+                        tp[(cl + ((3 + rot) & 3)) * PP] = r1 ? b0 : b3;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                team_sync();
+                if (tt == 0) {
+                    tma_bulk_s2g(outp + (size_t)f * Cfg::TILE_FLOATS, smem_u32(tile), Cfg::TILE_FLOATS * 4);
+                    store_pending = true;
+                }
+            }
+            ++it;
+            cur = s_pop[team * 2 + (it & 1)];   // written before the team barriers of the flush
+            curbuf ^= 1;
+        }
+        strip_release_rows<NR>(passed, d.Y1, row_base, d.Y0, lane, twarp == 0, B);
+        team_sync();
+        if (tt == 0) mbar_arrive(B.uempty0 + 8 * us);
+    }
+    if (tt == 0 && store_pending) tma_store_wait_all();
+}
+
+static size_t strip14_smem_bytes() {
+    return (size_t)Strip14Cfg::NR * kRowFloats * 4 + Strip14Cfg::FIXED + 16 * Strip14Cfg::NR;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -714,12 +1052,12 @@ bool roi_strip_supported(int C, int PH, int PW, int mode, int L) {
 
 template <int P>
 static int strip_launch(StripArgs &a, const RoiLevels &lv, cudaStream_t st, const StripWs &w, char *ws) {
-    using Cfg = StripCfg<P>;
     static bool attr_done[kNuhtcMaxDevices] = {false};
     const int dev = nuhtc_device();
-    const size_t smem = strip_smem_bytes<P>();
+    const size_t smem = P == 7 ? strip7_smem_bytes() : strip14_smem_bytes();
     if (!attr_done[dev]) {
-        NUHTC_CUDA(cudaFuncSetAttribute(roi_align_strip_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (P == 7) NUHTC_CUDA(cudaFuncSetAttribute(roi_align_strip7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else NUHTC_CUDA(cudaFuncSetAttribute(roi_align_strip14_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev] = true;
     }
     NUHTC_CUDA(cudaMemsetAsync(ws + w.counters, 0, w.cursor - w.counters, st));
@@ -731,7 +1069,8 @@ static int strip_launch(StripArgs &a, const RoiLevels &lv, cudaStream_t st, cons
     NUHTC_LAUNCH_CHECK();
     strip_records_kernel<P><<<gblocks, 256, 0, st>>>(a);
     NUHTC_LAUNCH_CHECK();
-    roi_align_strip_kernel<P><<<nuhtc_sm_count(), Cfg::NTHREADS, smem, st>>>(a);
+    if (P == 7) roi_align_strip7_kernel<<<nuhtc_sm_count(), Strip7Cfg::NTHREADS, smem, st>>>(a);
+    else roi_align_strip14_kernel<<<nuhtc_sm_count(), Strip14Cfg::NTHREADS, smem, st>>>(a);
     NUHTC_LAUNCH_CHECK();
     (void)lv;
     return NUHTC_OK;
