@@ -490,7 +490,9 @@ __global__ void __launch_bounds__(Strip7Cfg::NTHREADS, 1) roi_align_strip7_kerne
     const int cw = (tid >> 5) - 1, lane = tid & 31;
     const bool worker = lane < 28;
     const int q = lane & 3, pw = worker ? lane >> 2 : 0;
-    const bool odd = (pw & 1) != 0;   // this lane keeps its HIGH slice in register set 0
+    // this lane keeps its HIGH slice in register set 0; the four idle lanes share a quarter-warp with column 6 (even: low
+    // half of its cell) and must read a high half, or that phase of every tap load is a 2-way bank conflict
+    const bool odd = worker ? (pw & 1) != 0 : true;
     float *tile = s_tile + cw * Cfg::TILE_FLOATS;
     Rec *recs = s_rec + cw * 2;
     const uint32_t rf0 = B.rfull0 + 8 * (cw * 2);
@@ -555,71 +557,90 @@ __global__ void __launch_bounds__(Strip7Cfg::NTHREADS, 1) roi_align_strip7_kerne
                 const int nx = worker ? (int)R.nx[pw] : 0;
                 const int xoff = R.x0 - d.X0 + (worker ? (int)R.xs[pw] : 0);
                 const float *wxp = R.wx[pw];
-                // register set 0 reads this float offset inside a cell, set 1 the other half of the 128-byte line
-                const float *colp = s_ring + (size_t)xoff * kCG + (odd ? 16 : 0) + 4 * q;
-                const int d1 = odd ? -16 : 16;
+                // register set 0 reads this float offset inside a cell, set 1 the other half of the 128-byte line.  All
+                // addresses are 32-bit shared-window addresses (explicit ld.shared: no generic-pointer conversion per load)
+                const uint32_t col0 = smem_u32(s_ring) + (uint32_t)((xoff * kCG + (odd ? 16 : 0) + 4 * q) * 4);
+                const int d1 = odd ? -64 : 64;
+                const uint32_t wyd0 = smem_u32(&R.wyd[0][0]);
                 const int sB = R.sB, eA = R.eA;   // rows [sB, hh) feed bins 4-6, rows [0, eA) feed bins 0-3
-                // GRP 1: bins 0-3, 2: bins 4-6, 3: all.  NX is the warp's tap count; a lane with fewer taps repeats its
-                // last cell with weight 0 (a cell of its own bin: a padded tap never touches memory the lane does not own)
-                auto rows = [&](auto NXC, auto GRPC, int j0, int r0, int r1) {
-                    constexpr int NX = decltype(NXC)::value, GRP = decltype(GRPC)::value;
+                // ONE row loop per tap width (3 or 4: a lane with fewer taps repeats its own last cell with weight 0, so a
+                // padded tap never touches memory the lane does not own): the code the 15 warps run at their different
+                // places has to fit the instruction cache -- twelve specialised sweeps did not (26 % of the stall samples
+                // were instruction fetches, profiles/r02_roialign_strip.md).  The bin group a row feeds is a warp-uniform
+                // run-time test.
+                auto sweep = [&](auto NXC, int j0) {
+                    constexpr int NX = decltype(NXC)::value;
                     float wx[NX];
                     int toff[NX];
 #pragma unroll
                     for (int j = 0; j < NX; ++j) {
                         const bool ok = j0 + j < nx;
                         wx[j] = ok ? wxp[j0 + j] : 0.f;
-                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG;
+                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG * 4;
                     }
+                    unsigned sl = pos0 % NR;
+                    uint32_t rowp = col0 + sl * (uint32_t)(kRowFloats * 4);
+                    uint32_t wyp = wyd0;
 #pragma unroll 1
-                    for (int rc = r0; rc < r1; rc += 4) {
-                        const int nrow = min(4, r1 - rc);
+                    for (int rc = 0; rc < hh; rc += 4) {
+                        const int nrow = min(4, hh - rc);
                         if (lane < nrow) {
                             const unsigned gg = pos0 + rc + lane;
                             mbar_wait(B.full0 + 8 * (gg % NR), (gg / NR) & 1);
                         }
                         __syncwarp();
-                        unsigned sl = (pos0 + rc) % NR;
 #pragma unroll 1
                         for (int r = rc; r < rc + nrow; ++r) {
-                            const float *row = colp + (size_t)sl * kRowFloats;
-                            float4 v[2][NX];
+                            const bool gA = r < eA, gB = r >= sB;
+                            if (gA || gB) {
+                                float4 v[2][NX];
 #pragma unroll
-                            for (int s = 0; s < 2; ++s)
+                                for (int s = 0; s < 2; ++s)
 #pragma unroll
-                                for (int j = 0; j < NX; ++j) v[s][j] = *reinterpret_cast<const float4 *>(row + toff[j] + s * d1);
-                            const float4 wa = *reinterpret_cast<const float4 *>(&R.wyd[r][0]);
-                            const float4 wb = *reinterpret_cast<const float4 *>(&R.wyd[r][4]);
-                            float2 t[2][2];
+                                    for (int j = 0; j < NX; ++j) v[s][j] = lds_f4(rowp + toff[j] + s * d1);
+                                float2 t[2][2];
 #pragma unroll
-                            for (int s = 0; s < 2; ++s) {
-                                t[s][0] = t[s][1] = make_float2(0.f, 0.f);
+                                for (int s = 0; s < 2; ++s) {
+                                    t[s][0] = t[s][1] = make_float2(0.f, 0.f);
 #pragma unroll
-                                for (int j = 0; j < NX; ++j) {
-                                    t[s][0] = ffma2(wx[j], make_float2(v[s][j].x, v[s][j].y), t[s][0]);
-                                    t[s][1] = ffma2(wx[j], make_float2(v[s][j].z, v[s][j].w), t[s][1]);
+                                    for (int j = 0; j < NX; ++j) {
+                                        t[s][0] = ffma2(wx[j], make_float2(v[s][j].x, v[s][j].y), t[s][0]);
+                                        t[s][1] = ffma2(wx[j], make_float2(v[s][j].z, v[s][j].w), t[s][1]);
+                                    }
+                                }
+                                if (gA) {
+                                    const float4 wa = lds_f4(wyp);
+#pragma unroll
+                                    for (int s = 0; s < 2; ++s)
+#pragma unroll
+                                        for (int h = 0; h < 2; ++h) {
+                                            acc[s][0][h] = ffma2(wa.x, t[s][h], acc[s][0][h]);
+                                            acc[s][1][h] = ffma2(wa.y, t[s][h], acc[s][1][h]);
+                                            acc[s][2][h] = ffma2(wa.z, t[s][h], acc[s][2][h]);
+                                            acc[s][3][h] = ffma2(wa.w, t[s][h], acc[s][3][h]);
+                                        }
+                                }
+                                if (gB) {
+                                    const float4 wb = lds_f4(wyp + 16);
+#pragma unroll
+                                    for (int s = 0; s < 2; ++s)
+#pragma unroll
+                                        for (int h = 0; h < 2; ++h) {
+                                            acc[s][4][h] = ffma2(wb.x, t[s][h], acc[s][4][h]);
+                                            acc[s][5][h] = ffma2(wb.y, t[s][h], acc[s][5][h]);
+                                            acc[s][6][h] = ffma2(wb.z, t[s][h], acc[s][6][h]);
+                                        }
                                 }
                             }
-#pragma unroll
-                            for (int s = 0; s < 2; ++s)
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    if (GRP & 1) {
-                                        acc[s][0][h] = ffma2(wa.x, t[s][h], acc[s][0][h]);
-                                        acc[s][1][h] = ffma2(wa.y, t[s][h], acc[s][1][h]);
-                                        acc[s][2][h] = ffma2(wa.z, t[s][h], acc[s][2][h]);
-                                        acc[s][3][h] = ffma2(wa.w, t[s][h], acc[s][3][h]);
-                                    }
-                                    if (GRP & 2) {
-                                        acc[s][4][h] = ffma2(wb.x, t[s][h], acc[s][4][h]);
-                                        acc[s][5][h] = ffma2(wb.y, t[s][h], acc[s][5][h]);
-                                        acc[s][6][h] = ffma2(wb.z, t[s][h], acc[s][6][h]);
-                                    }
-                                }
-                            if (++sl == NR) sl = 0;
+                            rowp += kRowFloats * 4;
+                            wyp += 32;
+                            if (++sl == NR) {
+                                sl = 0;
+                                rowp -= (uint32_t)NR * kRowFloats * 4;
+                            }
                         }
                         // ---- rows behind the sweep go back to the producer
-                        if (single && rc == rel) {   // the swept stretch is contiguous with what is already released
+                        if (single) {
                             if (!hold_known) {
                                 // ONE lane probes the next record's barrier and reads its window top; the warp takes that
                                 // lane's answer (32 separate probes can straddle the phase flip and disagree, and a warp
@@ -634,28 +655,18 @@ __global__ void __launch_bounds__(Strip7Cfg::NTHREADS, 1) roi_align_strip7_kerne
                             }
                             const int lim = min(rc + nrow, hold);
                             __syncwarp();   // every lane has read the rows
-                            if (lim > rel) {
-                                if (lane < lim - rel) mbar_arrive(B.empty0 + 8 * ((pos0 + rel + lane) % NR));
+                            if (lim > rel) {   // at most 4 + what an earlier chunk could not release yet: 16 lanes suffice twice over
+                                for (int r2 = rel + lane; r2 < lim; r2 += 32) mbar_arrive(B.empty0 + 8 * ((pos0 + r2) % NR));
                                 rel = lim;
                             }
                         }
                     }
                 };
-                auto sweep = [&](auto NXC, int j0) {
-                    const int a1 = min(sB, eA), b0 = max(sB, eA);
-                    rows(NXC, std::integral_constant<int, 1>{}, j0, 0, a1);
-                    rows(NXC, std::integral_constant<int, 3>{}, j0, sB, eA);   // empty unless sB < eA
-                    rows(NXC, std::integral_constant<int, 2>{}, j0, b0, hh);
-                };
                 // bins wider than 4 taps take further sweeps over taps 4.., 8.. (one call site: the sweep code exists once)
 #pragma unroll 1
                 for (int j0 = 0; j0 < nxu; j0 += 4) {
-                    switch (nxu - j0 < 4 ? nxu - j0 : 4) {
-                        case 1: sweep(std::integral_constant<int, 1>{}, j0); break;
-                        case 2: sweep(std::integral_constant<int, 2>{}, j0); break;
-                        case 3: sweep(std::integral_constant<int, 3>{}, j0); break;
-                        default: sweep(std::integral_constant<int, 4>{}, j0); break;
-                    }
+                    if (nxu - j0 <= 3) sweep(std::integral_constant<int, 3>{}, j0);
+                    else sweep(std::integral_constant<int, 4>{}, j0);
                 }
             }
             passed = max(passed, y0 + rel);
@@ -820,7 +831,9 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
                 const int xoff = R.x0 - d.X0 + (worker ? (int)R.xs[pw] : 0);
                 const float *wxp = R.wx[pw];
                 const unsigned slot0 = (unsigned)(row_base + y0 - d.Y0) % NR;
-                const float *colp = s_ring + (size_t)xoff * kCG + 4 * q;
+                // 32-bit shared-window addresses (explicit ld.shared: no generic-pointer conversion per load)
+                const uint32_t col0 = smem_u32(s_ring) + (uint32_t)((xoff * kCG + 4 * q) * 4);
+                const uint32_t wyd0 = smem_u32(&R.wyd[0][0]);
                 // GRP bit g: bins 4g .. 4g+3
                 auto rows = [&](auto NXC, auto GRPC, int j0, int r0, int r1_) {
                     constexpr int NX = decltype(NXC)::value, GRP = decltype(GRPC)::value;
@@ -830,16 +843,17 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
                     for (int j = 0; j < NX; ++j) {
                         const bool ok = j0 + j < nx;
                         wx[j] = ok ? wxp[j0 + j] : 0.f;
-                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG;   // a padded tap repeats the lane's own last cell
+                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG * 4;   // a padded tap repeats the lane's own last cell
                     }
                     unsigned sl = slot0 + r0;
                     if (sl >= NR) sl -= NR;
+                    uint32_t rowp = col0 + sl * (uint32_t)(kRowFloats * 4);
+                    uint32_t wyp = wyd0 + (uint32_t)r0 * 64;
 #pragma unroll 1
                     for (int r = r0; r < r1_; ++r) {
-                        const float *row = colp + (size_t)sl * kRowFloats;
                         float4 v[NX];
 #pragma unroll
-                        for (int j = 0; j < NX; ++j) v[j] = *reinterpret_cast<const float4 *>(row + toff[j]);
+                        for (int j = 0; j < NX; ++j) v[j] = lds_f4(rowp + toff[j]);
                         float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int j = 0; j < NX; ++j) {
@@ -849,7 +863,7 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
 #pragma unroll
                         for (int gI = 0; gI < 4; ++gI) {
                             if (GRP & (1 << gI)) {
-                                const float4 w = *reinterpret_cast<const float4 *>(&R.wyd[r][4 * gI]);
+                                const float4 w = lds_f4(wyp + 16 * gI);
                                 const float ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
@@ -860,7 +874,12 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
                                 }
                             }
                         }
-                        if (++sl == NR) sl = 0;
+                        rowp += kRowFloats * 4;
+                        wyp += 64;
+                        if (++sl == NR) {
+                            sl = 0;
+                            rowp -= (uint32_t)NR * kRowFloats * 4;
+                        }
                     }
                 };
                 auto sweep = [&](auto NXC, int j0) {
