@@ -1033,8 +1033,9 @@ NUHTC_API int nuhtc_roi_align_cg32(const float *const *feats, const int *H, cons
         const int *left = nullptr, *left_count = nullptr;
         const int rc = roi_strip_forward(lv, B, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, ws, ws_bytes,
                                          st, &left, &left_count);
-        if (rc != NUHTC_OK) return rc;
-        return launch_sep_cg32(lv, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, left, left_count);
+        if (rc == NUHTC_OK)
+            return launch_sep_cg32(lv, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, left, left_count);
+        if (rc != 1) return rc;   // 1: the levels are too large for the strip binning -> every RoI through the per-RoI kernel
     }
     return launch_sep_cg32(lv, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, nullptr, nullptr);
 }

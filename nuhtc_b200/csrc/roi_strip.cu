@@ -41,6 +41,7 @@ constexpr int kRMax = 18;                             // tallest staged window
 constexpr int kNU = 4;                                // unit descriptors in flight
 constexpr int kRowFloats = kBW * kCG;
 constexpr int kSmemMax = 232448;                      // 227 KB opt-in shared memory per CTA
+constexpr int kScanSmemMax = 200 * 1024;              // the scan kernel stages the key histogram in shared memory
 
 // One record per staged RoI, written by the prepass at the RoI's sorted position and fetched with one bulk copy: the x tap
 // tables and the dense per-row y weights in the reference's fp32 op order ("staging of sampling coordinates").
@@ -181,10 +182,16 @@ __global__ void __launch_bounds__(1024) strip_scan_kernel(StripArgs a) {
         s_units = 0;
     }
     __syncthreads();
-    for (int base = 0; base < a.nkeys; base += 1024) {
-        const int i = base + tid;
-        const int v = i < a.nkeys ? a.hist[i] : 0;
-        int x = v;
+    {   // the histogram is staged in shared memory (coalesced both ways); every thread owns a contiguous run of keys:
+        // local sum, one block scan of the 1024 partial sums, local write-back
+        extern __shared__ int s_h[];
+        for (int i = tid; i < a.nkeys; i += 1024) s_h[i] = a.hist[i];
+        __syncthreads();
+        const int per = (a.nkeys + 1023) / 1024;
+        const int k0 = min(a.nkeys, tid * per), k1 = min(a.nkeys, k0 + per);
+        int sum = 0;
+        for (int i = k0; i < k1; ++i) sum += s_h[i];
+        int x = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, x, o);
@@ -202,14 +209,19 @@ __global__ void __launch_bounds__(1024) strip_scan_kernel(StripArgs a) {
             s_warp[lane] = t;
         }
         __syncthreads();
-        const int excl = s_carry + (wid ? s_warp[wid - 1] : 0) + x - v;
-        if (i < a.nkeys) {
-            a.hist[i] = excl;
-            a.cursor[i] = excl;
+        int run = (wid ? s_warp[wid - 1] : 0) + x - sum;
+        for (int i = k0; i < k1; ++i) {
+            const int v = s_h[i];
+            s_h[i] = run;
+            run += v;
         }
+        if (tid == 1023) s_carry = s_warp[31];
         __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
-        __syncthreads();
+        for (int i = tid; i < a.nkeys; i += 1024) {
+            const int v = s_h[i];
+            a.hist[i] = v;
+            a.cursor[i] = v;
+        }
     }
     if (tid == 0) a.hist[a.nkeys] = s_carry;
     __syncthreads();
@@ -307,23 +319,33 @@ __global__ void __launch_bounds__(256) strip_records_kernel(StripArgs a) {
         *reinterpret_cast<float4 *>(&rec->wx[lane][0]) = make_float4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<float4 *>(&rec->wx[lane][4]) = make_float4(w[4], w[5], w[6], w[7]);
     }
-    // dense y weights: wyd[r][p] = w_p[y0 + r - first_p] where bin p reaches window row r, else 0
+    // dense y weights: wyd[r][p] = w_p[y0 + r - first_p] where bin p reaches window row r, else 0.  The bin lanes park
+    // their tables in shared memory; then lane r assembles window row r and writes it with 128-bit stores.
     constexpr int WYS = StripRec<P>::WYS;
-    for (int e = lane; e < g.hh * WYS; e += 32) (&rec->wyd[0][0])[e] = 0.f;
-    __syncwarp();
+    __shared__ float s_wy[8][P][kMaxTap];
+    __shared__ int s_fn[8][P][2];
+    const int wib = threadIdx.x >> 5;
     const bool ybin = lane >= 16 && lane < 16 + P;
     if (ybin) {
         const int p = lane - 16;
-        for (int r = 0; r < g.hh; ++r) {
-            const int jj = g.y0 + r - first;
-            if ((unsigned)jj < (unsigned)n) {
-                float v = 0.f;
 #pragma unroll
-                for (int j = 0; j < kMaxTap; ++j)
-                    if (j == jj) v = w[j];
-                rec->wyd[r][p] = v;
+        for (int j = 0; j < kMaxTap; ++j) s_wy[wib][p][j] = w[j];
+        s_fn[wib][p][0] = first - g.y0;
+        s_fn[wib][p][1] = n;
+    }
+    __syncwarp();
+    if (lane < g.hh) {
+        float row[WYS];
+#pragma unroll
+        for (int p = 0; p < WYS; ++p) {
+            row[p] = 0.f;
+            if (p < P) {
+                const int jj = lane - s_fn[wib][p][0];
+                if ((unsigned)jj < (unsigned)s_fn[wib][p][1]) row[p] = s_wy[wib][p][jj];
             }
         }
+#pragma unroll
+        for (int p = 0; p < WYS; p += 4) *reinterpret_cast<float4 *>(&rec->wyd[lane][p]) = make_float4(row[p], row[p + 1], row[p + 2], row[p + 3]);
     }
     // bin groups: rows [gs, ge) reach group g = bins 4g .. 4g+3
     int gs[4], ge[4];
@@ -1084,7 +1106,12 @@ static int strip_launch(StripArgs &a, const RoiLevels &lv, cudaStream_t st, cons
     const unsigned gblocks = (unsigned)((a.K + warps_per_block - 1) / warps_per_block);
     strip_keys_kernel<P><<<gblocks, 256, 0, st>>>(a);
     NUHTC_LAUNCH_CHECK();
-    strip_scan_kernel<<<1, 1024, 0, st>>>(a);
+    static bool scan_attr[kNuhtcMaxDevices] = {false};
+    if (!scan_attr[dev]) {
+        NUHTC_CUDA(cudaFuncSetAttribute(strip_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemMax));
+        scan_attr[dev] = true;
+    }
+    strip_scan_kernel<<<1, 1024, (size_t)a.nkeys * sizeof(int), st>>>(a);
     NUHTC_LAUNCH_CHECK();
     strip_records_kernel<P><<<gblocks, 256, 0, st>>>(a);
     NUHTC_LAUNCH_CHECK();
@@ -1112,6 +1139,7 @@ int roi_strip_forward(const RoiLevels &lv, int B, int C, const float *rois, int 
         a.lv[l].data = lv.data[l];
         a.lv[l].scale = lv.scale[l];
     }
+    if ((size_t)a.nkeys * sizeof(int) > (size_t)kScanSmemMax) return 1;   // maps too large for the binning: per-RoI kernel
     const StripWs w = strip_ws_layout(K, a.nkeys, a.nbins, P);
     if (ws_bytes < w.total || !ws_) {
         nuhtc_set_error("roi_align: workspace %zu < %zu bytes", ws_bytes, w.total);
