@@ -31,6 +31,11 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
+def trace(msg):
+    if os.environ.get("NUHTC_BENCH_TRACE") == "1":
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 METRIC = "wsi_tiles_per_sec_roi_stage_plus_merge"
 UNIT = "tiles/s"
 
@@ -52,6 +57,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
+    p.add_argument("--no-slide", action="store_true", help="skip the whole-slide leg (BASELINE configs[3] + configs[4])")
+    p.add_argument("--no-extra", action="store_true", help="skip the extra roofline entries (routed proposals, PanNuke shape)")
     p.add_argument("--inflight", type=int, default=3, help="batches in flight: consecutive steps alternate between this many "
                    "streams (each with its own captured graph), so the latency-bound tail of one batch (NMS scans, mask NMS, "
                    "contours) overlaps the RoIAlign of the next; 1 = strictly one step after another")
@@ -294,11 +301,12 @@ def run_ours(args):
     stage = RoIStage(cfg, heads.bbox_heads(), heads.mask_head)
     timers = EventTimers()
     stage.timer = timers
-    # nuclei of the K*B tiles this rank processes: a stripe of the slide, `B` tiles wide, `steps` tile-rows tall
+    # the nuclei of the steps*B tiles this rank processes form a stripe of the slide, `B` tiles wide and `steps` tile rows
+    # tall: the merge at the end of the timed region runs on the contours the steps themselves traced
     from nuhtc_b200.slide import merge_sharded
-    slide = synth.slide_nuclei(B, args.steps * world, per_tile=23, seed=0)
-    shard = nb.slide.shard_by_rows(slide, rank, world)
-    xy, voff, score = (torch.from_numpy(shard[k]).to(dev) for k in ("xy", "voff", "score"))
+    D_slots = B * args.max_per_img
+    acc = NucleiAccumulator(args.steps, D_slots, cfg.contour_max_pts, B, rank, world, dev)
+    merged = {}
 
     def one_step():
         # every batch brings new FPN features: RoIStage.run stages the kernel layout itself, once per batch (timed as
@@ -307,12 +315,19 @@ def run_ours(args):
 
     def merge_step():
         with timers("merge"):
-            return merge_sharded(xy, voff, score, shard, rank, world, 0.05)
+            ring_xy, voff, score, shard = acc.rings()
+            merged["nuclei"] = int(score.numel())
+            return merge_sharded(ring_xy, voff, score, shard, rank, world, 0.05)
 
-    for _ in range(max(args.warmup, 3)):
+    trace("warm-up steps")
+    for i in range(max(args.warmup, 3)):
         res = one_step()
+        acc.collect(i % args.steps, res)
+    torch.cuda.synchronize()
+    trace("warm-up merge")
     merge_step()
     torch.cuda.synchronize()
+    trace("capture")
 
     # The step is launch bound on the host (~150 small torch ops + ~20 C-ABI calls): it is captured once into a CUDA
     # graph and replayed.  The captured work is exactly one_step() (NHWC staging, 4 RoIAlign launches, NMS, paste,
@@ -327,13 +342,14 @@ def run_ours(args):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         _lib.LAUNCHES["n"] = 0
-        graphs = []
+        graphs, graph_res = [], []
         for _ in range(max(1, args.inflight)):
             _lib.LAUNCHES["n"] = 0
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 res = one_step()
             graphs.append(g)
+            graph_res.append(res)
         graph = graphs[0]
         launches_per_step = _lib.LAUNCHES["n"]
         for g in graphs:
@@ -342,6 +358,7 @@ def run_ours(args):
         torch.cuda.synchronize()
     lanes = [torch.cuda.Stream() for _ in range(max(1, args.inflight))] if (graph is not None and args.inflight > 1) else []
 
+    trace("timed region")
     # ---- timed region: exactly K steps + the one merge
     sampler = ClockSampler(local, enabled=(rank == 0))   # NVML is initialised here, outside the timed region
     _lib.LAUNCHES["n"] = 0
@@ -358,10 +375,13 @@ def run_ours(args):
             if lanes:                                   # step i on lane i % inflight; a lane replays its own graph in order
                 with torch.cuda.stream(lanes[i % len(lanes)]):
                     graphs[i % len(lanes)].replay()
+                    acc.collect(i, graph_res[i % len(lanes)])
             elif graph is not None:
                 graph.replay()
+                acc.collect(i, graph_res[0])
             else:
                 res = one_step()
+                acc.collect(i, res)
         for ln in lanes:
             main.wait_stream(ln)
         e_steps = torch.cuda.Event(enable_timing=True)
@@ -372,6 +392,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
     ms = e0.elapsed_time(e1)
+    trace(f"timed region done: {ms:.1f} ms, merged {merged.get('nuclei')} nuclei")
     steps_ms = e0.elapsed_time(e_steps)   # this rank's K steps without the merge (the merge waits for the slowest rank)
     per_rank_steps = [steps_ms]
     if world > 1:
@@ -390,8 +411,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     i0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         res = one_step()
+        acc.collect(i, res)
     merge_step()
     i1.record()
     torch.cuda.synchronize()
@@ -418,11 +440,13 @@ def run_ours(args):
     roofline = None
     if ra_ms:
         ach = alg / (ra_ms * 1e-3) / 1e9
-        roofline = {"kernel": "roi_align_pipe_kernel<7,64,1,5,32,1> (7x7 bbox RoIAlign, K=%d, C=%d)" % (K, C), "bound": "hbm",
+        roofline = {"kernel": "roi_align_strip7_kernel + its 3 prepass launches (7x7 bbox RoIAlign, K=%d, C=%d)" % (K, C), "bound": "hbm",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the
-                    # `ncu --set full` capture summarised in profiles/r01_roialign_pipe.md (274.1 MB + 752.7 MB)
-                    "traffic": 1026811136 if (K == 16000 and C == 256 and args.dist == "nuclei") else None,
+                    # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch of the strip kernel
+                    # on this workload, from the `ncu --set full` capture summarised in profiles/r02_roialign_strip.md
+                    # (291.2 MB + 748.5 MB); null for any other shape
+                    "traffic": 1039640832 if (K == 16000 and C == 256 and args.dist == "nuclei") else None,
+                    "traffic_source": "profiles/r02_roialign_strip.md (ncu capture of the same launch shape, not this run)",
                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ra_ms, "launches_timed": len(ra) - ra_dropped,
                     "host_stall_samples_dropped": ra_dropped, "peak_source": peak_src}
     paste = op_ms.get("paste", [])
@@ -449,10 +473,22 @@ def run_ours(args):
     # per step: (trimmed) mean bracket x brackets per step
     breakdown = {k: trimmed_mean(v)[0] * len(v) / args.steps for k, v in op_ms.items() if len(v)}
 
+    # ---- extra roofline entries (N = 1 only): the routed proposal distribution and the shipping PanNuke shape
+    if rank == 0 and world == 1 and not args.no_extra:
+        trace("extra rooflines")
+        extra.update(extra_rooflines(args, feats, feats_h, dev, peak))
+    # ---- whole-slide leg: BASELINE configs[3] (43 264 tiles of a 40k x 40k slide, batches of 16 per GPU) + configs[4]
+    # (cross-tile merge of the ~1.7 M nuclei of that slide), once per rank
+    slide_leg = None
+    if not args.no_slide and graph is not None:
+        trace("slide leg")
+        slide_leg = run_slide(args, graphs, lanes, dev, rank, world)
+    trace("e2e")
+
     # ---- e2e: pinned host inputs copied every step, results read back every step
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, world, (xy, voff, score, shard, rank))
+        e2e = run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, world, rank)
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -469,11 +505,12 @@ def run_ours(args):
                 "config": {"workload": workload_name(args), "tiles_per_step_per_gpu": B, "proposals_per_tile": args.proposals,
                            "channels": C, "max_per_img": args.max_per_img, "detections_per_step": D, "mask_lane": args.lane,
                            "heads": "seeded stand-ins (stock cuDNN heads are outside the target)",
-                           "merge": "once per run over the nuclei of all steps*tiles tiles, inside the timed region",
-                           "nuclei_merged_per_gpu": int(score.numel()), "nuclei_kept": int(kept.numel()) if kept is not None else None,
+                           "merge": "once per run, inside the timed region, over the contours the timed steps traced (mask-NMS survivors of "
+                                    "all steps*tiles tiles laid out as a slide stripe at stride 192)",
+                           "nuclei_merged_per_gpu": merged.get("nuclei"), "nuclei_kept": int(kept.numel()) if kept is not None else None,
                            "l2": "inputs larger than L2 (356 MB FPN levels + 0.8 GB RoIAlign output per launch)",
                            "parallelism": f"tile stripes over {world} GPU(s), seam nuclei all-gathered for the merge"},
-                "roofline": roofline, "roofline_other": extra, "breakdown_ms_per_step": breakdown,
+                "roofline": roofline, "roofline_other": extra, "slide": slide_leg, "breakdown_ms_per_step": breakdown,
                 "per_rank_steps_ms": [round(v, 3) for v in per_rank_steps],
                 "timing": {"timed_region": ("cuda graph replay of the captured step" + (f", {len(lanes)} batches in flight on {len(lanes)} streams"
                                                                                           if lanes else "")) if graph is not None else "eager",
@@ -487,13 +524,154 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+class NucleiAccumulator:
+    """The nuclei the timed steps produce, kept on the device for the cross-tile merge: after every step the traced
+    contours of the mask-NMS survivors (RoIStageResult.contour_xy / contour_count), their scores and tile indices are
+    copied into the slab of that step.  Step s of rank r is tile row r*steps + s of the slide, `tiles` tiles wide at
+    stride 192 (infer_wsi.py: --patch_size 256 --step_size 192), so nuclei of neighbouring tiles meet in the 64 px overlap."""
+
+    def __init__(self, steps, D, max_pts, tiles, rank, world, dev, stride=192, tile=256):
+        self.steps, self.D, self.tiles, self.rank, self.world, self.stride, self.tile = steps, D, tiles, rank, world, stride, tile
+        self.xy = torch.zeros((steps, D, max_pts, 2), dtype=torch.int32, device=dev)
+        self.cnt = torch.zeros((steps, D), dtype=torch.int32, device=dev)
+        self.score = torch.zeros((steps, D), dtype=torch.float32, device=dev)
+        self.tile_idx = torch.full((steps, D), -1, dtype=torch.int32, device=dev)
+        self.row = (rank * steps + torch.arange(steps, device=dev, dtype=torch.int32))[:, None].expand(steps, D)
+
+    def collect(self, step, res):
+        self.xy[step].copy_(res.contour_xy, non_blocking=True)
+        self.cnt[step].copy_(res.contour_count, non_blocking=True)
+        self.score[step].copy_(res.det_scores, non_blocking=True)
+        self.tile_idx[step].copy_(res.det_tile, non_blocking=True)
+
+    def rings(self):
+        """-> (ring_xy fp64 [sumV,2], voff [n+1], score fp64 [n], shard meta for the multi-GPU merge)."""
+        import nuhtc_b200 as nb
+        n_all = self.steps * self.D
+        t = self.tile_idx.reshape(-1)
+        origin = torch.stack([t.clamp(min=0) * self.stride, self.row.reshape(-1) * self.stride], dim=1).to(torch.int32).contiguous()
+        sel = (t >= 0) & (self.cnt.reshape(-1) > 0)
+        ring_xy, voff, index = nb.rings_for_merge(self.xy.reshape(n_all, -1, 2), self.cnt.reshape(-1), select=sel, origin=origin)
+        # scores of different steps repeat (the stand-in heads are seeded tensors): a 1e-12-scale term keyed on the global
+        # nucleus index makes them distinct, as the merge contract asks (ties are the only thing it leaves open)
+        gid = index + self.rank * n_all
+        score = self.score.reshape(-1)[index].to(torch.float64) + gid.to(torch.float64) * 1e-12
+        tile_id = (self.row.reshape(-1)[index].to(torch.int64) * self.tiles + t[index].to(torch.int64))
+        shard = dict(gid=gid, tile_id=tile_id, tiles_x=self.tiles, tiles_y=self.steps * self.world, stride=self.stride, tile=self.tile,
+                     rows=(self.rank * self.steps, (self.rank + 1) * self.steps))
+        return ring_xy, voff, score, shard
+
+
+def _time_ms(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return float(np.median([x.elapsed_time(y) for x, y in evs]))
+
+
+def extra_rooflines(args, feats, feats_h, dev, peak):
+    """Roofline entries beside the headline one, timed alone with CUDA events (median of 10 launches after 3 warm-ups):
+    the 'routed' proposal distribution (all four FPN levels, windows up to the whole map) and the shipping PanNuke shape
+    (configs/nuhtc/htc_lite_swin_pytorch_fpn_PanNuke_seasaw_CAS.py: AttentionRoIExtractor, 64 channels, 7x7, sampling_ratio 2:
+    RoIAlign of levels 0,1 summed + cosine-attention pooling of levels 2,3 added at the store)."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    from nuhtc_b200.roi_extractors import AttentionRoIExtractor
+    out = {}
+    B, C = args.tiles, args.channels
+    scales = [1 / s for s in synth.FPN_STRIDES]
+    staged = nb.stage_levels(feats)
+    rois = synth.proposals(B, args.proposals, "routed", frame=512, seed=1).to(dev)
+    K = rois.shape[0]
+    o = torch.empty(K, C, 7, 7, device=dev)
+    ms = _time_ms(lambda: nb.roi_align_levels(staged, rois, 7, scales, 0, mode="route", out=o))
+    nbytes = roi_align_bytes(K, C, 7, feats_h, sorted(set(nb_levels(rois.cpu()))))
+    out["roi_align_bbox_routed"] = {"achieved": nbytes / ms / 1e6, "unit": "GB/s", "frac": nbytes / ms / 1e6 / peak,
+                                    "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": ms,
+                                    "note": "side log-U(16,512) px: every FPN level, windows up to the whole map (large windows take the per-RoI kernel)"}
+    del o, staged
+    f64 = [f.to(dev) for f in synth.fpn_levels(B, 64, frame=512, seed=2)]
+    rois_n = synth.proposals(B, args.proposals, "nuclei", frame=512, seed=2).to(dev)
+    ext = AttentionRoIExtractor(roi_layer=dict(type="RoIAlign", output_size=7, sampling_ratio=2), out_channels=64,
+                                featmap_strides=list(synth.FPN_STRIDES), start_level=2, thres=0)
+    ms = _time_ms(lambda: ext(f64, rois_n))
+    nbytes = rois_n.shape[0] * 64 * 49 * 4 + sum(f.numel() * 4 for f in f64) + rois_n.shape[0] * 20
+    out["pannuke_attention_extractor"] = {"achieved": nbytes / ms / 1e6, "unit": "GB/s", "frac": nbytes / ms / 1e6 / peak,
+                                          "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": ms,
+                                          "note": "whole AttentionRoIExtractor.forward (layout staging + 2 attention-pool launches + "
+                                                  "level-sum RoIAlign with the pooled bias), C=64, 7x7, sampling_ratio=2, K=%d" % rois_n.shape[0]}
+    return out
+
+
+def run_slide(args, graphs, lanes, dev, rank, world):
+    """BASELINE configs[3]: a 40k x 40k slide = 208 x 208 tiles of 256 px at stride 192 (43 264 tiles, 2 704 batches of 16),
+    sharded by tile rows; every rank replays its share of batches through the captured RoI-stage step (stage layout, 3 + 1
+    RoIAlign, NMS, paste, mask NMS, contours).  configs[4]: the cross-tile merge of the slide's ~1.7 M synthetic nuclei
+    (duplicates in the 64 px overlap bands), each rank holding its stripe, seam nuclei exchanged over NCCL."""
+    import torch.distributed as dist
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    from nuhtc_b200.slide import merge_sharded, stripe_rows
+    tiles_side = 208
+    r0, r1 = stripe_rows(tiles_side, rank, world)
+    my_tiles = (r1 - r0) * tiles_side
+    batches = (my_tiles + args.tiles - 1) // args.tiles
+    slide = synth.slide_nuclei(tiles_side, tiles_side, per_tile=23, seed=208)
+    shard = nb.slide.shard_by_rows(slide, rank, world)
+    xy, voff, score = (torch.from_numpy(shard[k]).to(dev) for k in ("xy", "voff", "score"))
+    total_nuclei = int(len(slide["score"]))
+    del slide
+    merge_sharded(xy, voff, score, shard, rank, world, 0.05)   # warm-up (allocator, NCCL channels)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    main = torch.cuda.current_stream()
+    e0.record()
+    for ln in lanes:
+        ln.wait_stream(main)
+    for i in range(batches):
+        if lanes:
+            with torch.cuda.stream(lanes[i % len(lanes)]):
+                graphs[i % len(lanes)].replay()
+        else:
+            graphs[0].replay()
+    for ln in lanes:
+        main.wait_stream(ln)
+    e1.record()
+    kept = merge_sharded(xy, voff, score, shard, rank, world, 0.05)
+    e2.record()
+    torch.cuda.synchronize()
+    t_stage, t_merge = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    nk = torch.tensor([int(kept.numel())], device=dev, dtype=torch.int64)
+    if world > 1:
+        t = torch.tensor([t_stage, t_merge], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_stage, t_merge = float(t[0]), float(t[1])
+        dist.all_reduce(nk)
+    tiles = tiles_side * tiles_side
+    return {"workload": "configs[3] 208x208 tiles (43264) through the RoI stage, batches of %d per GPU, + configs[4] merge of %d nuclei" % (args.tiles, total_nuclei),
+            "tiles": tiles, "batches_per_gpu": batches, "roi_stage_ms": t_stage, "merge_ms": t_merge,
+            "tiles_per_s": tiles / ((t_stage + t_merge) / 1e3), "merge_nuclei_per_s": total_nuclei / (t_merge / 1e3),
+            "nuclei": total_nuclei, "nuclei_kept": int(nk.item()),
+            "note": "every batch replays the same resident synthetic batch (inputs in HBM); max over ranks"}
+
+
 def nb_levels(rois_h, finest=56.0, L=4):
     """which FPN levels the synthetic RoIs touch (bytes accounting only; same rule as map_roi_levels)"""
     scale = torch.sqrt((rois_h[:, 3] - rois_h[:, 1]) * (rois_h[:, 4] - rois_h[:, 2]))
     return torch.floor(torch.log2(scale / finest + 1e-6)).clamp(0, L - 1).long().tolist()
 
 
-def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, world, merge_args):
+def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, world, rank):
     """Same step through the public API with HOST buffers.  Every step copies the FPN levels, the proposals and the head
     outputs from pinned host memory (H2D) and reads the per-tile results back into pinned host memory (D2H: detection
     slots, kept lists and the bit-row masks).  Two device buffer sets alternate so that the H2D of step i+1 and the D2H of
@@ -553,7 +731,7 @@ def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, worl
             S["graph"] = g
         S["host"] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outputs(S["res"])]
     d2h = sum(o.numel() * o.element_size() for o in sets[0]["host"])
-    xy, voff, score, shard, rank = merge_args
+    acc = NucleiAccumulator(steps, sets[0]["res"].det_boxes.shape[0], stage.cfg.contour_max_pts, args.tiles, rank, world, dev)
     torch.cuda.synchronize()
     # what the link gives for exactly these buffers (pure copies, nothing else running): the floor of an e2e step
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -586,6 +764,7 @@ def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, worl
             cur["graph"].replay()
         else:
             cur["res"] = compute(cur)
+        acc.collect(i, cur["res"])
         cur["ev_done"].record(main)
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(cur["ev_done"])
@@ -593,7 +772,8 @@ def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, worl
                 dst.copy_(src, non_blocking=True)
             cur["ev_out"].record(d2h_stream)
     main.wait_stream(d2h_stream)
-    kept = merge_sharded(xy, voff, score, shard, rank, world, 0.05)
+    ring_xy, voff, score, shard = acc.rings()
+    kept = merge_sharded(ring_xy, voff, score, shard, rank, world, 0.05)
     kept.cpu()
     e1.record()
     torch.cuda.synchronize()

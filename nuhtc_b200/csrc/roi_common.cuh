@@ -137,6 +137,29 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifdef NUHTC_WATCHDOG
+// debug build: a wait that lasts longer than ~2 s reports itself and traps (which barrier, which thread)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("STUCK block %d thread %d bar +0x%x parity %u\n", blockIdx.x, threadIdx.x, bar & 0x3ffff, parity);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -150,6 +173,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+#endif
 // 128-bit load from a 32-bit shared-window address
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
