@@ -356,6 +356,13 @@ def run_ours(args):
             for _ in range(2):
                 g.replay()
         torch.cuda.synchronize()
+        # warm-up of the merge at its timed size: all `steps` slabs filled, so the allocator and NCCL see the shapes of the
+        # timed region (a merge warmed up on 3 steps' nuclei paid cudaMalloc stalls of tens of ms inside the timed merge)
+        for i in range(args.steps):
+            graphs[i % len(graphs)].replay()
+            acc.collect(i, graph_res[i % len(graphs)])
+        merge_step()
+        torch.cuda.synchronize()
     lanes = [torch.cuda.Stream() for _ in range(max(1, args.inflight))] if (graph is not None and args.inflight > 1) else []
 
     trace("timed region")

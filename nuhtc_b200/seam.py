@@ -112,9 +112,9 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     N = score.numel()
     gid = torch.as_tensor(shard["gid"], dtype=torch.int64, device=dev)
     cnt = voff[1:] - voff[:-1]
-    seg = torch.repeat_interleave(torch.arange(N, device=dev), cnt)
-    ymin = torch.full((N,), float("inf"), dtype=torch.float64, device=dev).scatter_reduce(0, seg, xy[:, 1], "amin")
-    ymax = torch.full((N,), float("-inf"), dtype=torch.float64, device=dev).scatter_reduce(0, seg, xy[:, 1], "amax")
+    ycol = xy[:, 1].contiguous()
+    ymin = torch.segment_reduce(ycol, "min", lengths=cnt, unsafe=True)     # per-nucleus y extent: one segmented pass each
+    ymax = torch.segment_reduce(ycol, "max", lengths=cnt, unsafe=True)
     extents = [stripe_extent(shard, stripe_rows(shard["tiles_y"], q, world)) for q in range(world)]
 
     # ---- band = own nuclei that reach into another rank's stripe
@@ -175,19 +175,13 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     else:
         a_score, a_gid, a_cnt, a_xy = score, gid, cnt, xy
     M = N + H
-    # order the local set by global id so that equal scores are ranked like the single-GPU merge (lower index first)
-    perm = torch.argsort(a_gid, stable=True)
-    p_cnt = a_cnt[perm]
+    # The local set is own nuclei followed by the halo copies.  Scores are distinct by contract (ties are the one thing the
+    # reference leaves open: pandas' quicksort), so no re-ordering by global id is needed: the graph kernels rank by score.
     p_voff = torch.zeros(M + 1, dtype=torch.int64, device=dev)
-    p_voff[1:] = torch.cumsum(p_cnt, 0)
-    a_voff = torch.zeros(M + 1, dtype=torch.int64, device=dev)
-    a_voff[1:] = torch.cumsum(a_cnt, 0)
-    pseg = torch.repeat_interleave(torch.arange(M, device=dev), p_cnt)
-    psrc = a_voff[:-1][perm][pseg] + (torch.arange(int(p_voff[-1]), device=dev) - p_voff[:-1][pseg])
-    p_xy = a_xy[psrc].contiguous()
-    p_score = a_score[perm].contiguous()
-    inv = torch.empty_like(perm)
-    inv[perm] = torch.arange(M, device=dev)          # position of local-set element i in the permuted arrays
+    p_voff[1:] = torch.cumsum(a_cnt, 0)
+    p_xy = a_xy.contiguous()
+    p_score = a_score.contiguous()
+    inv = torch.arange(M, device=dev)                # position of local-set element i (kept for the index algebra below)
 
     mark("halo+permute")
     indeg, in_off, in_list = engine.graph(p_xy, p_voff, p_score, overlap_threshold)
@@ -203,16 +197,37 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     # iteration: every rank appends its count of undecided own nuclei (8 bytes) to its band states, so the termination test
     # rides on the state exchange instead of a separate all-reduce (on 8 GPUs every extra collective is another point where
     # the slowest host holds everybody up).
-    pcounts = [c + 8 for c in ncounts]
-    for _ in range(1 << 20):
-        remaining = engine.rounds(in_off, indeg, in_list, frozen, state, 8)
-        payload = torch.cat([state[band_pos], remaining.reshape(1).to(torch.int64).view(torch.uint8)])
-        g = _all_gather_ragged(payload, pcounts, group)
-        tot = torch.stack([x[-8:].clone().view(torch.int64) for x in g]).sum()
-        if H:
-            state[halo_pos] = torch.cat([x[:-8] for x in g])[halo_flat]
-        if int(tot.item()) == 0:
+    # Every rank sends one fixed-size message: [undecided own nuclei (int64) | band states | padding]; the halo copies
+    # read their owners' states straight out of the gathered buffer through an index computed once.
+    mx = 8 + max(max(ncounts), 1)
+    msg = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+    if H:
+        starts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+        starts[1:] = torch.cumsum(torch.as_tensor(ncounts, device=dev), 0)
+        hr = f_rank[halo_flat]
+        halo_src = hr * mx + 8 + (halo_flat - starts[hr])      # position of each halo nucleus' state in `gathered`
+    blind = 2          # iterations between two looks at the termination counter: the host only waits once per `blind` exchanges
+    done = False
+    for _ in range(1 << 18):
+        tots = []
+        for _k in range(blind):
+            remaining = engine.rounds(in_off, indeg, in_list, frozen, state, 8)
+            msg[:8] = remaining.reshape(1).to(torch.int64).view(torch.uint8)
+            if nb:
+                msg[8:8 + nb] = state[band_pos]
+            if hasattr(dist, "all_gather_into_tensor") and dev.type == "cuda":
+                dist.all_gather_into_tensor(gathered, msg, group=group)
+            else:
+                dist.all_gather(list(gathered.view(world, mx).unbind(0)), msg, group=group)
+            tots.append(gathered.view(world, mx)[:, :8].contiguous().view(torch.int64).sum())
+            if H:
+                state[halo_pos] = gathered[halo_src]
+        # an iteration that found nothing undecided anywhere leaves every later one a no-op, so any zero ends the loop
+        if int(torch.stack(tots).min().item()) == 0:
+            done = True
             break
+    assert done
     mark("resolve")
     if trace:
         print("seam trace (ms):", ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])),
