@@ -74,17 +74,22 @@ int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const int *W, c
  * [B][C/32][H][W][32] (nuhtc_to_cg32; 128-byte aligned): one 128-byte line per (cell, group of 32 channels), so a CTA that
  * owns 32 channels of a vertical strip of one image streams whole rows and serves every RoI of the strip from shared
  * memory -- each level row crosses L2->SM once per strip and channel group instead of once per overlapping RoI.
- * mode ROUTE (any L) or L == 1 take the strip kernel; RoIs whose sampling window cannot be staged (wider than 18 cells
- * on a level wider than 60 cells, taller than 20 rows, a bin with more than 8 taps) and mode SUM with L > 1 go
- * through the per-RoI kernel inside the same call.  Results are independent of the path (same fp32 tap tables).
- *   channels_last != 0: `in` is [B,H,W,C] (a channels_last tensor's memory), else [B,C,H,W].
- *   ws/ws_bytes from nuhtc_roi_align_workspace_bytes; no host synchronisation, CUDA-graph capturable. */
+ * mode ROUTE (any L) or L == 1 take the strip kernels; RoIs whose sampling window cannot be staged (wider than 18 cells
+ * on a level wider than 48 cells, taller than 18 rows, a bin with more than 8 taps) and mode SUM with L > 1 go
+ * through the per-RoI kernel inside the same call.  Results do not depend on the path (same fp32 tap tables).
+ *   nuhtc_to_cg32: channels_last != 0: `in` is [B,H,W,C] (a channels_last tensor's memory), else [B,C,H,W].
+ *   ws/ws_bytes from nuhtc_roi_align_workspace_bytes; no host synchronisation, CUDA-graph capturable.
+ *   pool2      NULL, or L host ints (mode SUM only): level l with pool2[l] != 0 enters the sum as
+ *              adaptive_avg_pool2d(RoIAlign(2PH x 2PW, sampling_ratio = 0), (PH, PW)) -- the semantic-feature branch of
+ *              NuHTC's _bbox_forward (nuhtc/models/htc_roi_head_cus.py:193-199) -- pooled directly at the output size
+ *              (the 2x2 average of bins with g samples per axis is one bin with 2g samples per axis). */
 #define NUHTC_LAYOUT_CG32 2
 int nuhtc_to_cg32(const float *in, float *out, int B, int C, int H, int W, int channels_last, void *stream);
 size_t nuhtc_roi_align_workspace_bytes(const int *H, const int *W, int L, int B, int K, int PH, int PW);
 int nuhtc_roi_align_cg32(const float *const *feats, const int *H, const int *W, const float *scale, int L, int B, int C,
                          const float *rois, int K, int PH, int PW, int sampling_ratio, int aligned, int mode,
-                         float finest_scale, float *out, const float *bias, void *ws, size_t ws_bytes, void *stream);
+                         float finest_scale, const int *pool2, float *out, const float *bias, void *ws, size_t ws_bytes,
+                         void *stream);
 
 /* ---- cosine-attention pooling (AttentionRoIExtractor, levels >= start_level) ---------------------------------------
  * Replaces nuhtc/models/roi_extractors_cus.py:220-238 for one level: for RoI k with centre cell

@@ -34,7 +34,7 @@ SIGNATURES = {
     "nuhtc_to_cg32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nuhtc_roi_align_workspace_bytes": (_sz, [_c.POINTER(_i), _c.POINTER(_i), _i, _i, _i, _i, _i]),
     "nuhtc_roi_align_cg32": (_i, [_c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_f), _i, _i, _i, _vp, _i, _i, _i, _i,
-                                  _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+                                  _i, _i, _f, _c.POINTER(_i), _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_attention_pool_workspace_bytes": (_sz, [_i, _i]),
     "nuhtc_attention_pool": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "nuhtc_nms_workspace_bytes": (_sz, [_i64, _i, _i64, _i]),

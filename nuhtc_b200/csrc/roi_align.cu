@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) roi_align_direct_kernel(RoiLevels lv, int
         }
         for (int l = l0; l < l1; ++l) {
             const int H = lv.H[l], W = lv.W[l];
-            const RoiGeom g = roi_geom(roi, lv.scale[l], PH, PW, sr, aligned);
+            const RoiGeom g = roi_geom(roi, lv.scale[l], PH, PW, sr, aligned, lv.pool2[l]);
             const float *plane;
             long sy, sx;
             if (layout == NUHTC_LAYOUT_NCHW) {
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
         const bool xb = tid < P, yb = tid >= 32 && tid < 32 + P;
         if (xb || yb) {
             const int l = mode == NUHTC_ROI_ROUTE ? route_level(roi, lv.L, finest) : it;
-            const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+            const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned, lv.pool2[l]);
             if (xb) {
                 build_axis_taps(g.start_w, g.bin_w, g.gw, tid, lv.W[l], 1.0f, s_wx + tid * kMaxTap, s_xs + tid, s_nx + tid);
                 if (tid == 0) {
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NQ *P *PHS, MINB) roi_align_sep_kernel(RoiLeve
             }
         } else {
             // ---- a bin of this thread is wider than the tap table (very large RoI): literal per-sample path
-            const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+            const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned, lv.pool2[l]);
 #pragma unroll 1
             for (int pi = 0; pi < PB; ++pi) {
                 const int ph = ph0 + pi;
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                 mbar_wait(tempty0 + 8 * slot, (use & 1) ^ 1);
                 PipeSlot<P> &sl = s_slot[slot];
                 const int l = mode == NUHTC_ROI_ROUTE ? route_level(roi, lv.L, finest) : it;
-                const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+                const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned, lv.pool2[l]);
                 const int H = lv.H[l], W = lv.W[l];
                 int first = 0, n = 0;
                 if (lane < P) {
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                         }
                     } else {
                         const float *roi = rois + (size_t)k * 5;
-                        const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned);
+                        const RoiGeom g = roi_geom(roi, lv.scale[l], P, P, sr, aligned, lv.pool2[l]);
     #pragma unroll 1
                         for (int pi = 0; pi < PB; ++pi) {
                             const int ph = ph0 + pi;
@@ -914,6 +914,7 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
         lv.H[l] = H[l];
         lv.W[l] = W[l];
         lv.scale[l] = scale[l];
+        lv.pool2[l] = 0;
     }
     cudaStream_t st = (cudaStream_t)stream;
     bool aligned16 = true;
@@ -1009,7 +1010,8 @@ NUHTC_API int nuhtc_to_cg32(const float *in, float *out, int B, int C, int H, in
 
 NUHTC_API int nuhtc_roi_align_cg32(const float *const *feats, const int *H, const int *W, const float *scale, int L, int B,
                                    int C, const float *rois, int K, int PH, int PW, int sampling_ratio, int aligned, int mode,
-                                   float finest_scale, float *out, const float *bias, void *ws, size_t ws_bytes, void *stream) {
+                                   float finest_scale, const int *pool2, float *out, const float *bias, void *ws, size_t ws_bytes,
+                                   void *stream) {
     NUHTC_CHECK_ARG(L >= 1 && L <= NUHTC_MAX_LEVELS, "roi_align_cg32: L=%d out of range", L);
     NUHTC_CHECK_ARG(PH == PW && (PH == 7 || PH == 14) && C >= 32 && C % 32 == 0 && B >= 0 && K >= 0,
                     "roi_align_cg32: needs PH == PW in {7, 14} and C %% 32 == 0 (PH=%d PW=%d C=%d)", PH, PW, C);
@@ -1025,6 +1027,8 @@ NUHTC_API int nuhtc_roi_align_cg32(const float *const *feats, const int *H, cons
         lv.H[l] = H[l];
         lv.W[l] = W[l];
         lv.scale[l] = scale[l];
+        lv.pool2[l] = pool2 ? pool2[l] : 0;
+        NUHTC_CHECK_ARG(lv.pool2[l] == 0 || mode == NUHTC_ROI_SUM, "roi_align_cg32: pool2 levels need mode SUM");
     }
     NUHTC_CHECK_ARG((uintptr_t)out % 16 == 0, "roi_align_cg32: out must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;

@@ -9,6 +9,7 @@ struct RoiLevels {
     int H[NUHTC_MAX_LEVELS];
     int W[NUHTC_MAX_LEVELS];
     float scale[NUHTC_MAX_LEVELS];
+    int pool2[NUHTC_MAX_LEVELS];   // != 0: this level is pooled at twice the output size and 2x2-averaged (see roi_geom)
     int L;
 };
 
@@ -37,7 +38,11 @@ struct RoiGeom {
     int b;
 };
 
-__device__ __forceinline__ RoiGeom roi_geom(const float *roi, float scale, int PH, int PW, int sr, int aligned) {
+// pool2: the level enters as `adaptive_avg_pool2d(RoIAlign(2PH x 2PW, sampling_ratio=0), (PH, PW))` -- the semantic branch of
+// NuHTC's _bbox_forward (nuhtc/models/htc_roi_head_cus.py:193-199).  Averaging the 2x2 bins of a (2PH x 2PW) RoIAlign with g
+// samples per bin and axis IS a (PH x PW) RoIAlign with 2g samples per bin and axis (same sample positions, one division by
+// 4*g*g), so the level is pooled directly at the output size with g = 2 * ceil(roi_extent / (2P)).
+__device__ __forceinline__ RoiGeom roi_geom(const float *roi, float scale, int PH, int PW, int sr, int aligned, int pool2 = 0) {
     RoiGeom g;
     const float off = aligned ? 0.5f : 0.0f;
     g.start_w = __fsub_rn(__fmul_rn(roi[1], scale), off);
@@ -51,8 +56,13 @@ __device__ __forceinline__ RoiGeom roi_geom(const float *roi, float scale, int P
     }
     g.bin_h = __fdiv_rn(rh, (float)PH);
     g.bin_w = __fdiv_rn(rw, (float)PW);
-    g.gh = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rh, (float)PH));
-    g.gw = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rw, (float)PW));
+    if (pool2) {
+        g.gh = 2 * (int)ceilf(__fdiv_rn(rh, (float)(2 * PH)));
+        g.gw = 2 * (int)ceilf(__fdiv_rn(rw, (float)(2 * PW)));
+    } else {
+        g.gh = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rh, (float)PH));
+        g.gw = sr > 0 ? sr : (int)ceilf(__fdiv_rn(rw, (float)PW));
+    }
     int c = g.gh * g.gw;
     if (c < 1) c = 1;
     g.count = (float)c;

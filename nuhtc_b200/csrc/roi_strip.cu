@@ -840,11 +840,12 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
             // every warp of the team first walks the `full` phases of the rows it leaves behind; only when ALL of them have
             // (team barrier) does warp 0 hand the rows back.  An arrival that ran ahead of a slower warp would let the
             // producer refill the slot twice before that warp looks at it, and a parity wait cannot tell phase n from n + 2.
-            if (passed < y0) {
-                strip_release_rows<NR>(passed, y0, row_base, d.Y0, lane, false, B);
+            // 16 rows at a time: a longer stretch waited for as a whole would wait for slots this very team still holds.
+            for (int base = passed; base < y0; base += 16) {
+                const int hi = min(base + 16, y0);
+                strip_release_rows<NR>(base, hi, row_base, d.Y0, lane, false, B);
                 team_sync();
-                if (twarp == 0)
-                    for (int r = passed + lane; r < y0; r += 32) mbar_arrive(B.empty0 + 8 * ((unsigned)(row_base + r - d.Y0) % NR));
+                if (twarp == 0 && base + lane < hi) mbar_arrive(B.empty0 + 8 * ((unsigned)(row_base + base + lane - d.Y0) % NR));
             }
             passed = max(passed, y0);
             {
@@ -971,10 +972,13 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
             cur = s_pop[team * 2 + (it & 1)];   // written before the team barriers of the flush
             curbuf ^= 1;
         }
-        strip_release_rows<NR>(passed, d.Y1, row_base, d.Y0, lane, false, B);
+        for (int base = passed; base < d.Y1; base += 16) {
+            const int hi = min(base + 16, d.Y1);
+            strip_release_rows<NR>(base, hi, row_base, d.Y0, lane, false, B);
+            team_sync();
+            if (twarp == 0 && base + lane < hi) mbar_arrive(B.empty0 + 8 * ((unsigned)(row_base + base + lane - d.Y0) % NR));
+        }
         team_sync();
-        if (twarp == 0)
-            for (int r = passed + lane; r < d.Y1; r += 32) mbar_arrive(B.empty0 + 8 * ((unsigned)(row_base + r - d.Y0) % NR));
         if (tt == 0) mbar_arrive(B.uempty0 + 8 * us);
     }
     if (tt == 0 && store_pending) tma_store_wait_all();

@@ -143,6 +143,16 @@ class StagedLevels:
     def __len__(self):
         return len(self.nchw)
 
+    def cat(self, other: "StagedLevels") -> "StagedLevels":
+        """these levels followed by `other`'s (same batch and channel count), e.g. FPN levels + the semantic feature map"""
+        assert other.B == self.B and other.C == self.C
+        o = object.__new__(StagedLevels)
+        o.B, o.C, o.device = self.B, self.C, self.device
+        o.shapes = self.shapes + other.shapes
+        o.nchw = self.nchw + other.nchw
+        o.cg32 = None if (self.cg32 is None or other.cg32 is None) else self.cg32 + other.cg32
+        return o
+
     def sub(self, idx: Sequence[int]) -> "StagedLevels":
         o = object.__new__(StagedLevels)
         o.B, o.C, o.device = self.B, self.C, self.device
@@ -158,7 +168,8 @@ def stage_levels(feats) -> StagedLevels:
 
 def roi_align_levels(feats, rois: torch.Tensor, output_size, spatial_scales: Sequence[float],
                      sampling_ratio: int = 0, aligned: bool = True, mode: str = "route", finest_scale: float = 56.0,
-                     impl: str = "auto", out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     impl: str = "auto", out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                     pool2: Optional[Sequence[bool]] = None) -> torch.Tensor:
     """All FPN levels in ONE call.
 
     mode 'route': each RoI is pooled on the level SingleRoIExtractor.map_roi_levels picks
@@ -166,6 +177,8 @@ def roi_align_levels(feats, rois: torch.Tensor, output_size, spatial_scales: Seq
     mode 'sum'  : every RoI is pooled on every level, results summed in level order
                   (AttentionRoIExtractor's RoIAlign branch, roi_extractors_cus.py:213-218,246).
     feats: NCHW fp32 CUDA tensors [B,C,H_l,W_l] (NCHW-contiguous or channels_last), or a ``StagedLevels``.
+    pool2: per level (mode 'sum'): the level enters as adaptive_avg_pool2d(RoIAlign(2P x 2P, sampling_ratio=0), P) -- the
+           semantic branch of NuHTC's _bbox_forward -- pooled directly at P x P inside the same launch.
     impl : 'auto' (strip-shared kernels on the CG32 layout when the shape allows, else the literal kernel),
            'direct' (literal per-sample kernel, bit-exact with the reference's accumulation order),
            'nhwc' (round-1 per-RoI kernels on the NHWC layout; kept for A/B measurements)."""
@@ -202,13 +215,16 @@ def roi_align_levels(feats, rois: torch.Tensor, output_size, spatial_scales: Seq
         ptrs = (ctypes.c_void_p * nl)(*[b.data_ptr() for b in bufs])
         wsb = lib.nuhtc_roi_align_workspace_bytes(Hs, Ws, nl, B, K, ph, pw)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        p2 = None if pool2 is None else (ctypes.c_int * nl)(*[int(bool(v)) for v in pool2])
         with torch.cuda.device(dev):
             rc = lib.nuhtc_roi_align_cg32(ptrs, Hs, Ws, sc, nl, B, C, rois.data_ptr(), K, ph, pw, int(sampling_ratio),
-                                          int(bool(aligned)), m, float(finest_scale), out.data_ptr(), L.ptr(bias), ws.data_ptr(),
+                                          int(bool(aligned)), m, float(finest_scale), p2, out.data_ptr(), L.ptr(bias), ws.data_ptr(),
                                           wsb, L.stream_ptr(dev))
         L.check(rc, "roi_align_cg32")
         L.count("roi_align_strip")
         return out
+    if pool2 is not None and any(pool2):
+        raise NotImplementedError("pool2 levels need the channel-group path (C % 32 == 0, 7x7 or 14x14 output)")
     use_nhwc = impl == "nhwc" and ph == pw and ph in (7, 14) and C % 64 == 0
     bufs = [to_nhwc(f) for f in raw] if use_nhwc else [f if f.is_contiguous() else f.contiguous() for f in raw]
     layout = L.LAYOUT_NHWC if use_nhwc else L.LAYOUT_NCHW

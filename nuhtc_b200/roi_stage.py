@@ -31,8 +31,14 @@ __all__ = ["RoIStageConfig", "RoIStage", "RoIStageResult", "delta2bbox", "bbox2r
 class RoIStageConfig:
     featmap_strides: Tuple[int, ...] = (4, 8, 16, 32)
     finest_scale: float = 56.0
-    extractor: str = "single"          # 'single': SingleRoIExtractor routing; 'sum': levels [0, sum_levels) summed
+    extractor: str = "single"          # 'single': SingleRoIExtractor routing; 'sum': levels [0, sum_levels) summed;
+                                       # 'attention': AttentionRoIExtractor = 'sum' + cosine-attention pooling of the levels
+                                       # from sum_levels on, added at the store (roi_extractors_cus.py:195-259)
     sum_levels: int = 2                # AttentionRoIExtractor pools levels 0,1 with RoIAlign (roi_extractors_cus.py:213-218)
+    attention_thres: float = 0.0       # AttentionRoIExtractor(thres=...)
+    semantic_fusion: Tuple[str, ...] = ()   # ('bbox', 'mask'): add the semantic RoI features (htc_roi_head_cus.py:193-199, 2332-2335)
+    semantic_stride: int = 4           # semantic_roi_extractor featmap_strides=[4]
+    semantic_out: int = 14             # its RoIAlign output size (sampling_ratio 0); pooled to bbox_out for the bbox branch
     bbox_out: int = 7
     bbox_sampling_ratio: int = 0       # stock HTC 0; NuHTC configs use 2
     mask_out: int = 14
@@ -54,6 +60,8 @@ class RoIStageConfig:
     min_area: int = 10                 # tools/infer_wsi.py --min_area
     mask_nms_thr: float = 0.05         # tools/infer_wsi.py:526
     dense_masks: bool = True           # True: [D,H,W] uint8 masks as get_seg_masks builds them; False: bit rows only
+    tile_postprocess: bool = True      # margin / min_area filter + per-tile mask NMS (+ contours) of tools/infer_wsi.py:510-534;
+                                       # False stops where the RoI head's simple_test stops (detections + pasted masks)
 
 
 @dataclass
@@ -184,8 +192,33 @@ class RoIStage:
                 self.trace.setdefault(k, []).append(v)
 
     # -- RoI extractors: one launch over all levels -------------------------------------------------------
-    def extract(self, feats: StagedLevels, rois: torch.Tensor, out_size: int, sampling_ratio: int) -> torch.Tensor:
+    def extract(self, feats: StagedLevels, rois: torch.Tensor, out_size: int, sampling_ratio: int, semantic: Optional[StagedLevels] = None,
+                branch: str = "bbox") -> torch.Tensor:
+        """`semantic`: the staged semantic feature map; when cfg.semantic_fusion names this branch its RoI features are
+        added INSIDE the same launch: as one more summed level (mask branch, same output size), or pooled at twice the
+        output size and 2x2-averaged (bbox branch: adaptive_avg_pool2d of the 14x14 semantic RoIAlign, folded into the
+        sampling grid -- see nuhtc_roi_align_cg32's pool2)."""
         cfg = self.cfg
+        fuse = semantic is not None and branch in cfg.semantic_fusion
+        if cfg.extractor == "attention":
+            from .mmcv_ops import attention_pool
+            L_all = min(len(feats), len(cfg.featmap_strides))
+            bias = None
+            for i in range(cfg.sum_levels, L_all):
+                # the reference hard-codes the level stride as 4 * 2**i (roi_extractors_cus.py:222)
+                bias = attention_pool(feats.nchw[i], rois, 4 * 2 ** i, float(cfg.attention_thres), out=bias)
+            lv = feats.sub(range(cfg.sum_levels))
+            scales = [1.0 / s_ for s_ in cfg.featmap_strides[: cfg.sum_levels]]
+            pool2 = [False] * cfg.sum_levels
+            if fuse:
+                assert cfg.semantic_out in (out_size, 2 * out_size), "semantic RoI size must equal the branch size or twice it"
+                lv = lv.cat(semantic)
+                scales = scales + [1.0 / cfg.semantic_stride]
+                pool2 = pool2 + [cfg.semantic_out == 2 * out_size]
+            return roi_align_levels(lv, rois, out_size, scales, sampling_ratio, True, mode="sum", bias=bias,
+                                    pool2=pool2 if any(pool2) else None)
+        if fuse:
+            raise NotImplementedError("semantic fusion is wired for extractor='attention' (the shipped NuHTC configs)")
         if cfg.extractor == "single":
             n = min(len(feats), len(cfg.featmap_strides))
             lv = feats.sub(range(n))
@@ -199,12 +232,15 @@ class RoIStage:
 
     # -- the stage ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def run(self, feats, rois: torch.Tensor, max_rois_per_tile: Optional[int] = None) -> RoIStageResult:
+    def run(self, feats, rois: torch.Tensor, max_rois_per_tile: Optional[int] = None,
+            semantic_feat: Optional[torch.Tensor] = None) -> RoIStageResult:
         """feats: the FPN levels of the batch ([B,C,H_l,W_l] fp32 CUDA tensors) or an already staged ``StagedLevels``.
-        The kernel layout is staged ONCE here and handed to the four RoIAlign calls explicitly (no cache involved)."""
+        The kernel layout is staged ONCE here and handed to the four RoIAlign calls explicitly (no cache involved).
+        semantic_feat [B,C,H/stride,W/stride]: the semantic head's feature map (cfg.semantic_fusion)."""
         cfg = self.cfg
         with self._t("stage_layout"):
             feats = stage_levels(feats)
+            sem = stage_levels([semantic_feat]) if (semantic_feat is not None and cfg.semantic_fusion) else None
         B = feats.B
         dev = rois.device
         K = rois.shape[0]
@@ -215,7 +251,7 @@ class RoIStage:
         bbox_pred = None
         for i in range(cfg.num_stages):
             with self._t("roi_align_bbox"):
-                bbox_feats = self.extract(feats, rois, cfg.bbox_out, cfg.bbox_sampling_ratio)
+                bbox_feats = self.extract(feats, rois, cfg.bbox_out, cfg.bbox_sampling_ratio, sem, "bbox")
             self._rec(bbox_rois=rois, bbox_feats=bbox_feats)
             cls_score, bbox_pred = self.bbox_heads[i](bbox_feats)
             ms_scores.append(cls_score)
@@ -260,7 +296,7 @@ class RoIStage:
 
         # mask branch: RoIAlign 14x14 on the detections (network frame), mask head, paste into the tile frame
         with self._t("roi_align_mask"):
-            mask_feats = self.extract(feats, mask_rois, cfg.mask_out, cfg.mask_sampling_ratio)
+            mask_feats = self.extract(feats, mask_rois, cfg.mask_out, cfg.mask_sampling_ratio, sem, "mask")
         self._rec(mask_rois=mask_rois, mask_feats=mask_feats)
         logits = self.mask_head(mask_feats, det_cand)
         probs = logits.sigmoid()
@@ -291,6 +327,11 @@ class RoIStage:
                     masks.record_stream(main)
         self._rec(paste_probs=probs, paste_boxes=det_boxes)
 
+        if not cfg.tile_postprocess:
+            if side is not None:
+                torch.cuda.current_stream(dev).wait_stream(side)
+            return RoIStageResult(det_boxes, det_scores, det_labels, det_tile, masks, bits, area, None, None, None,
+                                  det_valid=det_valid, det_cand=det_cand, status=(status,))
         # tools/infer_wsi.py:510-521 margin / min_area filter, then per-tile mask NMS (:526)
         tile_ids = det_ops.tile_filter(det_boxes, area, det_tile, cfg.margin, H, W, cfg.min_area)
         cap = cfg.max_per_img if cfg.max_per_img > 0 else max(D, 1)

@@ -7,6 +7,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+HERE_TESTS = os.path.dirname(os.path.abspath(__file__))
+if HERE_TESTS not in sys.path:      # test-side helpers: _slides.py, _toy_heads.py
+    sys.path.insert(0, HERE_TESTS)
 
 
 def pytest_configure(config):

@@ -199,3 +199,37 @@ def test_full_size_linearity_property():
     # and the fast kernel agrees with the literal kernel on a slice of the same launch shape
     sub = rois[::40].contiguous()
     assert (nb.roi_align(a, sub, 7, 0.25, 0) - nb.roi_align_levels([a], sub, 7, [0.25], 0, impl="direct")).abs().max().item() <= TOL
+
+
+@pytest.mark.parametrize("P", [7, 14])
+def test_strip_path_stress_sparse_repeated_concurrent(P):
+    """The strip kernels are persistent producer / consumer pipelines (TMA ring, mbarriers): exercise the schedules that
+    differ from the dense bench shape -- a handful of RoIs per image (consumers skip far more rows than the ring holds),
+    all four levels with large windows (leftover list), back-to-back launches on a warm L2, and three streams at once --
+    and hold every result to the literal kernel."""
+    import nuhtc_b200 as nb
+    from nuhtc_b200 import synth
+    B, C = 8, 64
+    feats = [f.cuda() for f in synth.fpn_levels(B, C, frame=512, seed=5)]
+    staged = nb.stage_levels(feats)
+    scales = [1 / s for s in synth.FPN_STRIDES]
+    cases = {"sparse": synth.proposals(B, 3, "nuclei", frame=512, seed=6), "routed": synth.proposals(B, 400, "routed", frame=512, seed=7),
+             "nuclei": synth.proposals(B, 600, "nuclei", frame=512, seed=8)}
+    refs = {}
+    for name, r in cases.items():
+        refs[name] = nb.roi_align_levels(feats, r.cuda(), P, scales, 0, mode="route", impl="direct")
+    for name, r in cases.items():
+        r = r.cuda()
+        outs = [nb.roi_align_levels(staged, r, P, scales, 0, mode="route") for _ in range(6)]   # no sync in between
+        for o in outs:
+            assert (o - refs[name]).abs().max().item() <= TOL, name
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    torch.cuda.synchronize()
+    res = []
+    for it in range(4):
+        for s, (name, r) in zip(streams, cases.items()):
+            with torch.cuda.stream(s):
+                res.append((name, nb.roi_align_levels(staged, r.cuda(), P, scales, 0, mode="route")))
+    torch.cuda.synchronize()
+    for name, o in res:
+        assert (o - refs[name]).abs().max().item() <= TOL, name

@@ -158,3 +158,20 @@ def test_stage_contours_feed_the_merge(oracle):
     ref = oracle.merge_overlap_arrays(xy, vo, np.array(sc, dtype=np.float64), 0.05)
     assert kept.tolist() == list(ref)
     assert 0 < len(ref) < len(polys)          # some nuclei of overlapping tiles were merged away
+
+
+def test_compact_remaps_per_tile_keep_lists():
+    """RoIStageResult.compact(): tile t's kept list sits at keep[tile_start[t] : +tile_count[t]] and tile_start is the scan
+    of the ENTRANT counts, so once a tile suppresses a mask the lists are not packed from 0: the remapped lists
+    must name the same detections as the raw ones, for every tile of a B > 1 batch."""
+    from nuhtc_b200.roi_stage import RoIStage
+    cfg, feats, rois, heads = _setup("single", 64, B=3, n_per=250, max_per_img=60)
+    gh = copy.copy(heads).to("cuda")
+    raw = RoIStage(cfg, gh.bbox_heads(), gh.mask_head).run([f.cuda() for f in feats], rois.cuda())
+    res = raw.compact()
+    a, b = raw.kept_indices(), res.kept_indices()
+    assert len(a) == len(b) == 3 and sum(len(x) for x in a) > 0
+    assert any(int(c) < 60 for c in raw.tile_count.cpu())          # some tile did lose masks: the gaps exist
+    for ka, kb in zip(a, b):
+        assert torch.equal(raw.det_boxes[ka], res.det_boxes[kb]) and torch.equal(raw.det_scores[ka], res.det_scores[kb])
+        assert torch.equal(raw.det_tile[ka], res.det_tile[kb])
