@@ -11,7 +11,9 @@ def patch_mmcv(verbose: bool = False):
     rebound attributes."""
     from . import RoIAlign, _do_paste_mask, batched_nms, nms, roi_align
     import mmcv.ops
-    import mmcv.ops.nms as mmcv_nms
+    # not `import mmcv.ops.nms as m`: mmcv/ops/__init__.py does `from .nms import nms`, so the attribute `mmcv.ops.nms` is
+    # the function and that form would bind the function, not the submodule
+    mmcv_nms = importlib.import_module("mmcv.ops.nms")
 
     done = []
 
