@@ -90,12 +90,127 @@ def _all_gather_ragged(t: torch.Tensor, counts: List[int], group) -> List[torch.
     return [o[:c] for o, c in zip(outs, counts)]
 
 
+def _ring_area(xy: torch.Tensor, voff: torch.Tensor) -> torch.Tensor:
+    """|shoelace| / 2 of every ring (closed or open), fp64."""
+    cnt = voff[1:] - voff[:-1]
+    n = xy.shape[0]
+    idx = torch.arange(n, device=xy.device)
+    seg = torch.repeat_interleave(torch.arange(cnt.numel(), device=xy.device), cnt)
+    nxt = torch.where(idx + 1 == voff[1:][seg], voff[:-1][seg], idx + 1)
+    cr = xy[:, 0] * xy[nxt, 1] - xy[nxt, 0] * xy[:, 1]
+    return torch.segment_reduce(cr, "sum", lengths=cnt, unsafe=True).abs() * 0.5
+
+
+def _best_per_group(group: torch.Tensor, area: torch.Tensor, score: torch.Tensor, gid: torch.Tensor):
+    """For every distinct value of `group`: the candidate with the largest area, ties to the better global rank (score
+    descending, then id) -- nuclei_merge.py:143-150 walks the hits in rank order and keeps the first maximum.  Returns
+    (group values, candidate positions)."""
+    p = torch.argsort(gid, stable=True)
+    p = p[torch.argsort(-score[p], stable=True)]
+    p = p[torch.argsort(-area[p], stable=True)]
+    p = p[torch.argsort(group[p], stable=True)]
+    g = group[p]
+    first = torch.ones(g.numel(), dtype=torch.bool, device=g.device)
+    first[1:] = g[1:] != g[:-1]
+    return g[first], p[first]
+
+
+def _area_picks(xy, voff, score, gid, a_score, a_gid, state, indeg, in_off, in_list, bidx, ncounts, rank, group):
+    """merge_strategy='area' (nuclei_merge.py:143-150): every kept nucleus q is replaced by the largest nucleus among those it
+    suppressed FIRST, i.e. among the suppressed c whose lowest-ranked kept suppressor is q.  Returns the flags of the own
+    nuclei that are in the final set.
+
+    Every suppressor of an own nucleus is in the local set, so owner(c) is a local computation.  The children of a kept q
+    live on q's rank or are band nuclei of other ranks; one more exchange of the band records -- each carrying its owner's
+    id, its own (area, score) and, for a kept nucleus, the best child found on its own rank -- lets every rank work out
+    the same pick for every kept band nucleus."""
+    dev = score.device
+    N, M = score.numel(), a_score.numel()
+    world = len(ncounts)
+    area = _ring_area(xy, voff)
+    o1 = torch.argsort(a_gid, stable=True)
+    order = o1[torch.argsort(-a_score[o1], stable=True)]            # local set in global rank order
+    lrank = torch.empty(M, dtype=torch.int64, device=dev)
+    lrank[order] = torch.arange(M, device=dev)
+    own_state = state[:N]
+    # ---- owner(c) of every suppressed own nucleus: the best-ranked kept entry of its suppressor list
+    deg = indeg[:N].to(torch.int64) * (own_state == 2)
+    dst = torch.repeat_interleave(torch.arange(N, device=dev), deg)
+    eoff = torch.cumsum(deg, 0) - deg
+    src = in_list[in_off[:N].to(torch.int64)[dst] + (torch.arange(dst.numel(), device=dev) - eoff[dst])].to(torch.int64)
+    live = state[src] == 1
+    big = torch.iinfo(torch.int64).max
+    owner_lrank = torch.full((N,), big, dtype=torch.int64, device=dev)
+    owner_lrank.scatter_reduce_(0, dst[live], lrank[src[live]], "amin")
+    child = (owner_lrank < big).nonzero().squeeze(1)
+    owner = order[owner_lrank[child]]                               # local-set index of each child's owner
+    owner_of = torch.full((N,), -1, dtype=torch.int64, device=dev)
+    owner_of[child] = owner
+    # ---- best own child of every local-set nucleus
+    lb = torch.full((M,), -1, dtype=torch.int64, device=dev)
+    if child.numel():
+        q, pos = _best_per_group(owner, area[child], score[child], gid[child])
+        lb[q] = child[pos]
+    # ---- band records of every rank
+    nb = bidx.numel()
+    rec = torch.full((nb, 8), -1.0, dtype=torch.float64, device=dev)
+    if nb:
+        rec[:, 0] = gid[bidx].to(torch.float64)
+        rec[:, 1] = score[bidx]
+        rec[:, 2] = area[bidx]
+        rec[:, 3] = own_state[bidx].to(torch.float64)
+        ob = owner_of[bidx]
+        rec[:, 4] = torch.where(ob >= 0, a_gid[ob.clamp(min=0)].to(torch.float64), rec[:, 4])
+        lbb = lb[bidx]
+        has = lbb >= 0
+        lc = lbb.clamp(min=0)
+        rec[:, 5] = torch.where(has, gid[lc].to(torch.float64), rec[:, 5])
+        rec[:, 6] = torch.where(has, area[lc], rec[:, 6])
+        rec[:, 7] = torch.where(has, score[lc], rec[:, 7])
+    T = torch.cat(_all_gather_ragged(rec, ncounts, group)) if sum(ncounts) else rec
+    t_rank = torch.repeat_interleave(torch.arange(world, device=dev), torch.as_tensor(ncounts, device=dev))
+    t_gid = T[:, 0].to(torch.int64)
+    # ---- candidates of the kept band nuclei: (a) best child on the owner's rank, (b) band children on other ranks
+    a_sel = (T[:, 3] == 1) & (T[:, 5] >= 0)
+    cand_q = [t_gid[a_sel]]
+    cand = [(T[a_sel, 6], T[a_sel, 7], T[a_sel, 5].to(torch.int64))]
+    b_sel = ((T[:, 3] == 2) & (T[:, 4] >= 0)).nonzero().squeeze(1)
+    if b_sel.numel():
+        sg, sp = torch.sort(t_gid)
+        og = T[b_sel, 4].to(torch.int64)
+        j = torch.searchsorted(sg, og).clamp(max=sg.numel() - 1)
+        found = sg[j] == og                                          # the owner is a band nucleus ...
+        foreign = found & (t_rank[sp[j]] != t_rank[b_sel])           # ... of another rank than the child's
+        b_sel = b_sel[foreign]
+        cand_q.append(og[foreign])
+        cand.append((T[b_sel, 2], T[b_sel, 1], t_gid[b_sel]))
+    cq = torch.cat(cand_q)
+    c_area, c_score, c_gid = (torch.cat([c[i] for c in cand]) for i in range(3))
+    flagged = torch.zeros(N, dtype=torch.bool, device=dev)
+    band = torch.zeros(N, dtype=torch.bool, device=dev)
+    band[bidx] = True
+    kept = own_state == 1
+    # kept nuclei away from the seam: children are all local
+    inner = kept & ~band
+    lbo = lb[:N]
+    flagged |= inner & (lbo < 0)
+    flagged[lbo[inner & (lbo >= 0)]] = True
+    # kept band nuclei: the pick comes out of the exchanged records (the same on every rank); the picked nucleus' own rank flags it
+    if cq.numel():
+        qg, pos = _best_per_group(cq, c_area, c_score, c_gid)
+        flagged |= torch.isin(gid, c_gid[pos])
+        flagged |= kept & band & ~torch.isin(gid, qg)
+    else:
+        flagged |= kept & band
+    return flagged
+
+
 def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor, shard: Dict, rank: int, world: int,
                       overlap_threshold: float = 0.05, merge_strategy: str = "probability", engine=None, group=None,
                       return_ids: bool = False):
     """Returns this rank's kept LOCAL indices (score-descending); with ``return_ids`` also their global nuclei_id."""
-    if merge_strategy != "probability":
-        raise NotImplementedError("the multi-GPU merge implements merge_strategy='probability' (the documented default)")
+    if merge_strategy not in ("probability", "area"):
+        raise ValueError(f"Invalid merge strategy: {merge_strategy}. Use 'probability' or 'area'.")
     from .slide import stripe_rows
     engine = engine or CudaMergeEngine()
     dev = xy.device
@@ -232,7 +347,12 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     if trace:
         print("seam trace (ms):", ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])),
               f"| own {N} band {nb} halo {H}", flush=True)
-    kept_local = (state[own_pos] == 1).nonzero().squeeze(1)
+    if merge_strategy == "area":
+        flagged = _area_picks(xy, voff, score, gid, a_score, a_gid, state, indeg, in_off, in_list, bidx, ncounts, rank, group)
+        mark("area picks")
+    else:
+        flagged = state[own_pos] == 1
+    kept_local = flagged.nonzero().squeeze(1)
     order = torch.argsort(-score[kept_local], stable=True)
     kept_local = kept_local[order]
     if not return_ids:

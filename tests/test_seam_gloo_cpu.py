@@ -61,7 +61,7 @@ class OracleEngine:
         return torch.tensor([rem], dtype=torch.int64)
 
 
-def _worker(rank, world, port, tiles, ret):
+def _worker(rank, world, port, tiles, strategy, ret):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -73,7 +73,7 @@ def _worker(rank, world, port, tiles, ret):
         slide = synth.slide_nuclei(tiles[0], tiles[1], per_tile=6, seed=4)
         sh = shard_by_rows(slide, rank, world)
         kept, ids = merge_distributed(torch.from_numpy(sh["xy"]), torch.from_numpy(sh["voff"]), torch.from_numpy(sh["score"]), sh,
-                                      rank, world, 0.05, engine=OracleEngine(), return_ids=True)
+                                      rank, world, 0.05, merge_strategy=strategy, engine=OracleEngine(), return_ids=True)
         ret[rank] = (sh["gid"][kept.numpy()].tolist(), ids.tolist())
     finally:
         dist.destroy_process_group()
@@ -87,15 +87,18 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("strategy", ["probability", "area"])
 @pytest.mark.parametrize("world,tiles", [(2, (3, 4)), (3, (2, 5)), (4, (2, 3))])   # the last one leaves rank 3 without tiles
-def test_distributed_merge_equals_single_process(oracle, world, tiles):
+def test_distributed_merge_equals_single_process(oracle, world, tiles, strategy):
     from nuhtc_b200 import synth
     slide = synth.slide_nuclei(tiles[0], tiles[1], per_tile=6, seed=4)
-    ref = oracle.merge_overlap_arrays(slide["xy"], slide["voff"], slide["score"], 0.05)
+    ref = oracle.merge_overlap_arrays(slide["xy"], slide["voff"], slide["score"], 0.05, strategy)
+    if strategy == "area":   # the two strategies keep different nuclei on this slide, some of them picked across the seam
+        assert ref.tolist() != oracle.merge_overlap_arrays(slide["xy"], slide["voff"], slide["score"], 0.05).tolist()
     assert len(ref) < len(slide["score"])  # there are cross-tile duplicates, some of them across the stripe seam
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), tiles, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), tiles, strategy, ret), nprocs=world, join=True)
     got = {}
     for r in range(world):
         gids, ids = ret[r]

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N tools/check_dist_merge.py [tiles_x tiles_y]: the N-GPU merge (NCCL seam exchange) must
+"""torchrun --nproc-per-node N tools/check_dist_merge.py [tiles_x tiles_y [probability|area]]: the N-GPU merge (NCCL seam exchange) must
 reproduce the single-GPU merge bit for bit (kept nuclei and their nuclei_id)."""
 import os
 import sys
@@ -18,6 +18,7 @@ from nuhtc_b200.slide import shard_by_rows
 
 def main():
     tx, ty = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (32, 32)
+    strategy = sys.argv[3] if len(sys.argv) > 3 else "probability"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -25,12 +26,12 @@ def main():
     slide = synth.slide_nuclei(tx, ty, per_tile=23, seed=7)
     sh = shard_by_rows(slide, rank, world)
     xy, voff, score = (torch.from_numpy(sh[k]).to(dev) for k in ("xy", "voff", "score"))
-    kept, ids = merge_distributed(xy, voff, score, sh, rank, world, 0.05, return_ids=True)   # warm-up (NCCL channels, allocator)
+    kept, ids = merge_distributed(xy, voff, score, sh, rank, world, 0.05, strategy, return_ids=True)   # warm-up (NCCL channels, allocator)
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    kept, ids = merge_distributed(xy, voff, score, sh, rank, world, 0.05, return_ids=True)
+    kept, ids = merge_distributed(xy, voff, score, sh, rank, world, 0.05, strategy, return_ids=True)
     e1.record()
     torch.cuda.synchronize()
     tms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -50,15 +51,15 @@ def main():
         allp = torch.cat([o[: int(c.item())] for o, c in zip(outs, ns)]).cpu().numpy()
         by_id = allp[np.argsort(allp[:, 1])]
         full = [torch.from_numpy(slide[k]).to(dev) for k in ("xy", "voff", "score")]
-        ref = nb.merge_arrays(*full, 0.05).cpu().numpy()
+        ref = nb.merge_arrays(*full, 0.05, strategy).cpu().numpy()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        nb.merge_arrays(*full, 0.05)
+        nb.merge_arrays(*full, 0.05, strategy)
         s1.record()
         torch.cuda.synchronize()
         ok = len(by_id) == len(ref) and (by_id[:, 1] == np.arange(len(ref))).all() and (by_id[:, 0] == ref).all()
         n_all = len(slide["score"])
-        print(f"dist-merge world={world} nuclei={n_all} kept={len(ref)} match={ok} | {world}-GPU merge {float(tms.item()):.2f} ms "
+        print(f"dist-merge[{strategy}] world={world} nuclei={n_all} kept={len(ref)} match={ok} | {world}-GPU merge {float(tms.item()):.2f} ms "
               f"({n_all / float(tms.item()) / 1e3:.1f} M nuclei/s), single-GPU merge {s0.elapsed_time(s1):.2f} ms", flush=True)
     dist.barrier()
     dist.destroy_process_group()
