@@ -437,7 +437,7 @@ struct RingPos {
 // consumer: staged rows for a thread with NX x-taps (NX == 0: runtime count, weights from the slot) and PB (<= 14)
 // output rows whose dense weights sit at wyd[row][0..7] (rows 0..6) and wyd[row][8..15] (rows 7..13)
 template <int NX, int PB, int NS, int WYS>
-__device__ __forceinline__ void staged_rows(const float *ring, int stage_floats, int CC, int y0, int y1, int xoff, int q,
+__device__ __forceinline__ void staged_rows(const float *ring, int stage_floats, int pixs, int y0, int y1, int toff,
                                             const float *s_wxp, const float *s_wyd, float2 (&acc)[PB][1][2], uint32_t full0,
                                             uint32_t empty0, RingPos &rp, int nx_rt, int my0, int my1) {
     constexpr int NXR = NX > 0 ? NX : 1;
@@ -448,18 +448,18 @@ __device__ __forceinline__ void staged_rows(const float *ring, int stage_floats,
     for (int y = y0; y < y1; ++y, s_wyd += WYS) {
         mbar_wait(full0 + 8 * rp.stage, rp.parity);
         if (y >= my0 && y < my1) {
-            const float *row = ring + (size_t)rp.stage * stage_floats + (size_t)xoff * CC + 4 * q;
+            const float *row = ring + (size_t)rp.stage * stage_floats + toff; // toff: the thread's first tap of this row
             float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
             if (NX > 0) {
 #pragma unroll
                 for (int j = 0; j < NX; ++j) {
-                    const float4 v = *reinterpret_cast<const float4 *>(row + (size_t)j * CC);
+                    const float4 v = *reinterpret_cast<const float4 *>(row + (size_t)j * pixs);
                     t0 = ffma2(wx[j], make_float2(v.x, v.y), t0);
                     t1 = ffma2(wx[j], make_float2(v.z, v.w), t1);
                 }
             } else {
                 for (int j = 0; j < nx_rt; ++j) {
-                    const float4 v = *reinterpret_cast<const float4 *>(row + (size_t)j * CC);
+                    const float4 v = *reinterpret_cast<const float4 *>(row + (size_t)j * pixs);
                     const float w = s_wxp[j];
                     t0 = ffma2(w, make_float2(v.x, v.y), t0);
                     t1 = ffma2(w, make_float2(v.z, v.w), t1);
@@ -490,7 +490,8 @@ template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
 __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
     roi_align_pipe_kernel(RoiLevels lv, int C, const float *__restrict__ rois, int K, int sr, int aligned, int mode, float finest,
                           float *__restrict__ out, const float *__restrict__ bias, int bulk_store_flag,
-                          const __grid_constant__ RoiTmaps tm) {
+                          const __grid_constant__ RoiTmaps tm, int cg32, const int *__restrict__ list,
+                          const int *__restrict__ list_count) {
     constexpr int CC = NQ * 4;
     constexpr int PP = SepCfg<P>::PP;
     // tile stride: the padded one is conflict-free for the transposition; the dense one (== PP) leaves as ONE asynchronous
@@ -528,8 +529,11 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
 
     const int nchunk = C / CC;
     const int nlev = mode == NUHTC_ROI_ROUTE ? 1 : lv.L;
-    const long nunits = K; // a unit = one RoI: its levels are consecutive items, its channel chunks share the item's tables
-                           // (nchunk > 1 is only launched with nlev == 1)
+    // a unit = one RoI (of the device-side list when there is one: the strip kernel's leftovers): its levels are consecutive
+    // items, its channel chunks share the item's tables (nchunk > 1 is only launched with nlev == 1)
+    const long nunits = list ? *list_count : K;
+    // channel-group layout [b][C/32][y][x][32]: a stage holds the CC/32 groups of a row one after the other, [g][WMAX][32]
+    constexpr int GPC = CC / 32 > 0 ? CC / 32 : 1;
     unsigned itemctr = 0;
     constexpr int WYS = (P + 6) / 7 * 8;
     static_assert(PB <= 7 || (PB == P && P <= 14), "a consumer owns at most 7 output rows, or all of them");
@@ -554,11 +558,19 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                         const int c0 = chunk * CC;
                         const float *src0 = lv.data[l] + (((size_t)b * H + y0) * W + x0) * (size_t)C + c0;
                         const int pix0 = (b * H + y0) * W + x0;
+                        // channel-group layout: lane g < GPC copies the row segment of group chunk*GPC + g (ww * 128 contiguous bytes)
+                        const float *srcg = lv.data[l] + ((((size_t)b * (C / 32) + chunk * GPC + (lane < GPC ? lane : 0)) * H + y0) * W + x0) * 32;
                         for (int y = y0; y < y1; ++y, rp.next<NS>()) {
                             const unsigned stage = rp.stage;
                             mbar_wait(empty0 + 8 * stage, rp.parity ^ 1u);
                             const uint32_t dst = smem_u32(s_ring + (size_t)stage * STAGE_FLOATS);
-                            if (lane == 0) {
+                            if (cg32) {
+                                if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)ww * 128u * GPC);
+                                __syncwarp();
+                                if (lane < GPC)
+                                    tma_bulk_g2s(dst + (uint32_t)lane * WMAX * 128u, srcg + (size_t)(y - y0) * W * 32, (uint32_t)ww * 128u,
+                                                 full0 + 8 * stage);
+                            } else if (lane == 0) {
                                 if (nchunk == 1) { // the row segment is contiguous in NHWC: one plain bulk copy
                                     mbar_arrive_expect_tx(full0 + 8 * stage, (uint32_t)ww * CC * 4);
                                     tma_bulk_g2s(dst, src0 + (size_t)(y - y0) * rstride, (uint32_t)ww * CC * 4, full0 + 8 * stage);
@@ -578,7 +590,7 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
         // =========================== tap warp: tables + window geometry, kPipeSlots items ahead ===========================
         const int lane = tid - NCONS;
         for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-            const int k = (int)unit;
+            const int k = list ? list[unit] : (int)unit;
             const float *roi = rois + (size_t)k * 5;
             for (int it = 0; it < nlev; ++it, ++itemctr) {
                 const unsigned slot = itemctr % kPipeSlots, use = itemctr / kPipeSlots;
@@ -744,21 +756,26 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                         const int xoff = sl.xs[pw] - sl.x0;
                         if (nx <= 0) { my0 = 0; my1 = 0; } // no valid sample in this column: still take part in the row barriers
                         const float *wyd = &sl.wyd[0][ph0 / 7 * 8];
+                        const int pixs = cg32 ? 32 : CC;
+                        const int toff = cg32 ? (q >> 3) * (WMAX * 32) + xoff * 32 + 4 * (q & 7) : xoff * CC + 4 * q;
                         switch (nx) {
-                            case 1: staged_rows<1, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                            case 2: staged_rows<2, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                            case 3: staged_rows<3, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                            case 4: staged_rows<4, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
-                            default: staged_rows<0, PB, NS, WYS>(s_ring, STAGE_FLOATS, CC, y0, y1, xoff, q, wxp, wyd, acc, full0, empty0, rp, nx > 0 ? nx : 0, my0, my1); break;
+                            case 1: staged_rows<1, PB, NS, WYS>(s_ring, STAGE_FLOATS, pixs, y0, y1, toff, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            case 2: staged_rows<2, PB, NS, WYS>(s_ring, STAGE_FLOATS, pixs, y0, y1, toff, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            case 3: staged_rows<3, PB, NS, WYS>(s_ring, STAGE_FLOATS, pixs, y0, y1, toff, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            case 4: staged_rows<4, PB, NS, WYS>(s_ring, STAGE_FLOATS, pixs, y0, y1, toff, wxp, wyd, acc, full0, empty0, rp, nx, my0, my1); break;
+                            default: staged_rows<0, PB, NS, WYS>(s_ring, STAGE_FLOATS, pixs, y0, y1, toff, wxp, wyd, acc, full0, empty0, rp, nx > 0 ? nx : 0, my0, my1); break;
                         }
                     }
                 } else if (worker) {
                     const int H = lv.H[l], W = lv.W[l];
-                    const float *img = lv.data[l] + (size_t)sl.batch * H * W * C + c0 + 4 * q;
+                    const int cq = c0 + 4 * q;
+                    const size_t pix = cg32 ? 32 : (size_t)C;
+                    const float *img = cg32 ? lv.data[l] + (size_t)sl.batch * H * W * C + (size_t)(cq >> 5) * H * W * 32 + (cq & 31)
+                                            : lv.data[l] + (size_t)sl.batch * H * W * C + cq;
                     if (md == kPipeDirect) {
                         if (nx > 0 && my1 > my0) {
-                            const float *rowp = img + ((size_t)my0 * W + sl.xs[pw]) * (size_t)C;
-                            sweep_rows<0, PB, 1>(rowp, (size_t)W * C, (size_t)C, 0, my0, my1, wxp, wyp, ys, ny, acc, nx);
+                            const float *rowp = img + ((size_t)my0 * W + sl.xs[pw]) * pix;
+                            sweep_rows<0, PB, 1>(rowp, (size_t)W * pix, pix, 0, my0, my1, wxp, wyp, ys, ny, acc, nx);
                         }
                     } else {
                         const float *roi = rois + (size_t)k * 5;
@@ -777,8 +794,8 @@ __global__ void __launch_bounds__((NQ *P *PHS + 31) / 32 * 32 + 64, MINB)
                                     const bool okx = axis_sample(sample_coord(g.start_w, g.bin_w, pw, ix, g.gw), W, xl, xh, lx, hx);
                                     if (!(oky && okx)) continue;
                                     const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-                                    const float4 v1 = ldg_f4(img + ((size_t)yl * W + xl) * C), v2 = ldg_f4(img + ((size_t)yl * W + xh) * C);
-                                    const float4 v3 = ldg_f4(img + ((size_t)yh * W + xl) * C), v4 = ldg_f4(img + ((size_t)yh * W + xh) * C);
+                                    const float4 v1 = ldg_f4(img + ((size_t)yl * W + xl) * pix), v2 = ldg_f4(img + ((size_t)yl * W + xh) * pix);
+                                    const float4 v3 = ldg_f4(img + ((size_t)yh * W + xl) * pix), v4 = ldg_f4(img + ((size_t)yh * W + xh) * pix);
                                     a[0] += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
                                     a[1] += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
                                     a[2] += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
@@ -843,15 +860,17 @@ static bool build_tmaps(const RoiLevels &lv, int B, int C, int CC, RoiTmaps *tm)
 
 template <int P, int NQ, int PHS, int NS, int WMAX, int MINB>
 static int launch_pipe(const RoiLevels &lv, int B, int C, const float *rois, int K, int sr, int aligned, int mode, float finest,
-                       float *out, const float *bias, cudaStream_t st) {
+                       float *out, const float *bias, cudaStream_t st, int cg32 = 0, const int *list = nullptr,
+                       const int *list_count = nullptr) {
     static int grid_cache[kNuhtcMaxDevices] = {0};
     int &grid_cached = grid_cache[nuhtc_device()];
     static_assert(WMAX <= tmap_box_px(kTmapBoxes - 1) || true, "");
     RoiTmaps tm;
     memset(&tm, 0, sizeof tm);
-    if (C / (NQ * 4) > 1) {
+    if (C / (NQ * 4) > 1 && !cg32) {
         if (WMAX > tmap_box_px(kTmapBoxes - 1) || !build_tmaps(lv, B, C, NQ * 4, &tm)) return 1; // caller falls back
     }
+    if (cg32 && (NQ * 4) % 32 != 0) return 1;
     const size_t smem = sizeof(float) * ((size_t)NS * WMAX * NQ * 4 + NQ * 4 * ((P == 14 && NQ == 32) ? P * P : SepCfg<P>::S)) +
                         kPipeSlots * sizeof(PipeSlot<P>) +
                         sizeof(uint64_t) * (2 * NS + 2 * kPipeSlots) + 128;
@@ -870,7 +889,7 @@ static int launch_pipe(const RoiLevels &lv, int B, int C, const float *rois, int
     const long nunits = K;
     const int grid = (int)(nunits < grid_cached ? nunits : grid_cached);
     static const int bulk = getenv("NUHTC_RA_BULK") ? atoi(getenv("NUHTC_RA_BULK")) : 1;
-    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, bulk, tm);
+    kern<<<grid, nthreads, smem, st>>>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, bulk, tm, cg32, list, list_count);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }
@@ -981,9 +1000,25 @@ NUHTC_API int nuhtc_roi_align_fwd(const float *const *feats, const int *H, const
 
 
 // per-RoI kernel on the channel-group layout: every RoI (list == nullptr) or the RoIs of a device-side list
-static int launch_sep_cg32(const RoiLevels &lv, int C, const float *rois, int K, int P, int sr, int aligned, int mode,
+static int launch_sep_cg32(const RoiLevels &lv, int B, int C, const float *rois, int K, int P, int sr, int aligned, int mode,
                            float finest, float *out, const float *bias, cudaStream_t st, const int *list,
                            const int *list_count) {
+    // Pipelined kernel first: the window rows arrive through bulk copies (one per channel group and row), so a RoI's
+    // latency is one ring fill instead of a chain of dependent global loads per row.  NUHTC_RA_PIPE=0: A/B switch.
+    if (ra_pipe()) {
+        const int nlev = mode == NUHTC_ROI_ROUTE ? 1 : lv.L;
+        int rc = 1;
+        if (P == 7) {
+            if (C == 256) rc = launch_pipe<7, 64, 1, 5, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+            else if (C == 128) rc = launch_pipe<7, 32, 1, 8, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+            // C = 64 (the PanNuke configs' two-level sum): measured 0.72 ms pipelined vs 0.29 ms per-RoI on K = 16000 -> per-RoI
+        } else if (C % 128 == 0 && (C == 128 || nlev == 1)) { // 128-channel chunks: a chunk is its own output tile, so no level sum across chunks
+            rc = launch_pipe<14, 32, 1, 6, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+        } else if (C == 64) {
+            rc = launch_pipe<14, 16, 2, 8, 32, 1>(lv, B, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
+        }
+        if (rc != 1) return rc;
+    }
     if (P == 7) {
         if (C % 256 == 0) return launch_sep<7, 32, 1, 2, 2>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
         if (C % 128 == 0) return launch_sep<7, 16, 1, 2, 4>(lv, C, rois, K, sr, aligned, mode, finest, out, bias, st, 1, list, list_count);
@@ -1038,10 +1073,10 @@ NUHTC_API int nuhtc_roi_align_cg32(const float *const *feats, const int *H, cons
         const int rc = roi_strip_forward(lv, B, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, ws, ws_bytes,
                                          st, &left, &left_count);
         if (rc == NUHTC_OK)
-            return launch_sep_cg32(lv, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, left, left_count);
+            return launch_sep_cg32(lv, B, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, left, left_count);
         if (rc != 1) return rc;   // 1: the levels are too large for the strip binning -> every RoI through the per-RoI kernel
     }
-    return launch_sep_cg32(lv, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, nullptr, nullptr);
+    return launch_sep_cg32(lv, B, C, rois, K, PH, sampling_ratio, aligned, mode, finest_scale, out, bias, st, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ Forward (inference) only; GPU only.
 from __future__ import annotations
 
 import ctypes
+import os
 from collections import OrderedDict
 from typing import Optional, Sequence, Tuple
 
@@ -20,6 +21,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+
+_RA_STATS = os.environ.get("NUHTC_RA_STATS") == "1"
 
 __all__ = ["RoIAlign", "roi_align", "nms", "batched_nms", "roi_align_levels", "to_nhwc", "to_cg32", "clear_layout_cache",
            "layout_cache", "StagedLevels", "stage_levels",
@@ -222,6 +225,8 @@ def roi_align_levels(feats, rois: torch.Tensor, output_size, spatial_scales: Seq
                                           wsb, L.stream_ptr(dev))
         L.check(rc, "roi_align_cg32")
         L.count("roi_align_strip")
+        if _RA_STATS:   # debugging aid (synchronises): how many RoIs missed the strip kernel
+            print(f"RA_STATS P={ph} K={K} leftover={int(ws[8:12].view(torch.int32).item())}", flush=True)
         return out
     if pool2 is not None and any(pool2):
         raise NotImplementedError("pool2 levels need the channel-group path (C % 32 == 0, 7x7 or 14x14 output)")
