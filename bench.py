@@ -452,7 +452,7 @@ def run_ours(args):
                     # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch of the strip kernel
                     # on this workload, from the `ncu --set full` capture summarised in profiles/r02_roialign_strip.md
                     # (291.2 MB + 748.5 MB); null for any other shape
-                    "traffic": 1039640832 if (K == 16000 and C == 256 and args.dist == "nuclei") else None,
+                    "traffic": 1046130432 if (K == 16000 and C == 256 and args.dist == "nuclei") else None,
                     "traffic_source": "profiles/r02_roialign_strip.md (ncu capture of the same launch shape, not this run)",
                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ra_ms, "launches_timed": len(ra) - ra_dropped,
                     "host_stall_samples_dropped": ra_dropped, "peak_source": peak_src}
