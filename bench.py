@@ -56,6 +56,7 @@ def parse():
     p.add_argument("--cpu-tiles", type=int, default=2, help="tiles in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--host-wc", action="store_true", help="e2e leg: FPN levels in write-combined pinned host memory (A/B for the H2D rate at N > 1)")
     p.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of replaying a CUDA graph")
     p.add_argument("--no-slide", action="store_true", help="skip the whole-slide leg (BASELINE configs[3] + configs[4])")
     p.add_argument("--no-extra", action="store_true", help="skip the extra roofline entries (routed proposals, PanNuke shape)")
@@ -244,6 +245,17 @@ def cpu_sample(args, nthreads, tiles):
     return tiles / (t2 - t0), {"roi_stage_s": t1 - t0, "merge_s": t2 - t1}
 
 
+def workload_config(args, world):
+    """`config` of the JSON line: the workload only (identical for both arms), nothing measured."""
+    return {"workload": workload_name(args), "tiles_per_step_per_gpu": args.tiles, "proposals_per_tile": args.proposals,
+            "channels": args.channels, "max_per_img": args.max_per_img, "detections_per_step": args.tiles * args.max_per_img,
+            "mask_lane": args.lane, "heads": "seeded stand-ins (stock cuDNN heads are outside the target)",
+            "merge": "once per run, inside the timed region, over the contours the timed steps traced (mask-NMS survivors of "
+                     "all steps*tiles tiles laid out as a slide stripe at stride 192)",
+            "l2": "inputs larger than L2 (356 MB FPN levels + 0.8 GB RoIAlign output per launch)",
+            "parallelism": f"tile stripes over {world} GPU(s), seam nuclei all-gathered for the merge"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -259,7 +271,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_tiles / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "tiles_per_step": args.cpu_tiles},
+            "config": workload_config(args, args.gpus),   # the same workload as our arm; each step is a bounded sample of it (below)
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.cpu_tiles} tiles/step through oracle.stage.roi_stage_cpu (RoIAlign/paste split over "
                                        f"{cores} host threads; NMS / mask NMS / merge single-threaded like mmcv, pycocotools, shapely)"},
@@ -509,14 +521,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args), "tiles_per_step_per_gpu": B, "proposals_per_tile": args.proposals,
-                           "channels": C, "max_per_img": args.max_per_img, "detections_per_step": D, "mask_lane": args.lane,
-                           "heads": "seeded stand-ins (stock cuDNN heads are outside the target)",
-                           "merge": "once per run, inside the timed region, over the contours the timed steps traced (mask-NMS survivors of "
-                                    "all steps*tiles tiles laid out as a slide stripe at stride 192)",
-                           "nuclei_merged_per_gpu": merged.get("nuclei"), "nuclei_kept": int(kept.numel()) if kept is not None else None,
-                           "l2": "inputs larger than L2 (356 MB FPN levels + 0.8 GB RoIAlign output per launch)",
-                           "parallelism": f"tile stripes over {world} GPU(s), seam nuclei all-gathered for the merge"},
+                "config": workload_config(args, world),
+                "run": {"nuclei_merged_per_gpu": merged.get("nuclei"), "nuclei_kept": int(kept.numel()) if kept is not None else None},
                 "roofline": roofline, "roofline_other": extra, "slide": slide_leg, "breakdown_ms_per_step": breakdown,
                 "per_rank_steps_ms": [round(v, 3) for v in per_rank_steps],
                 "timing": {"timed_region": ("cuda graph replay of the captured step" + (f", {len(lanes)} batches in flight on {len(lanes)} streams"
@@ -678,6 +684,20 @@ def nb_levels(rois_h, finest=56.0, L=4):
     return torch.floor(torch.log2(scale / finest + 1e-6)).clamp(0, L - 1).long().tolist()
 
 
+def wc_pinned_like(t):
+    """Copy of a host tensor in write-combined pinned memory (cudaHostAlloc): the device reads it without snooping the CPU caches."""
+    import ctypes
+    from cuda.bindings import runtime as rt
+    nbytes = t.numel() * t.element_size()
+    err, ptr = rt.cudaHostAlloc(nbytes, rt.cudaHostAllocWriteCombined | rt.cudaHostAllocPortable)
+    if int(err) != 0:
+        raise RuntimeError(f"cudaHostAlloc failed: {err}")
+    buf = (ctypes.c_byte * nbytes).from_address(int(ptr))
+    out = torch.frombuffer(buf, dtype=t.dtype).view(t.shape)
+    out.copy_(t)
+    return out
+
+
 def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, world, rank):
     """Same step through the public API with HOST buffers.  Every step copies the FPN levels, the proposals and the head
     outputs from pinned host memory (H2D) and reads the per-tile results back into pinned host memory (D2H: detection
@@ -691,6 +711,8 @@ def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, worl
     from nuhtc_b200.slide import merge_sharded
     steps = args.e2e_steps or min(args.steps, 10)
     K = rois_h.shape[0]
+    if args.host_wc:
+        feats_h = [wc_pinned_like(f) for f in feats_h]
     main = torch.cuda.current_stream()
     h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     sets = []
@@ -739,6 +761,15 @@ def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, worl
         S["host"] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outputs(S["res"])]
     d2h = sum(o.numel() * o.element_size() for o in sets[0]["host"])
     acc = NucleiAccumulator(steps, sets[0]["res"].det_boxes.shape[0], stage.cfg.contour_max_pts, args.tiles, rank, world, dev)
+    # warm-up of the merge at the size of this leg's timed region (allocator blocks, NCCL buffers of these shapes)
+    for i in range(steps):
+        S = sets[i % 2]
+        if S["graph"] is not None:
+            S["graph"].replay()
+        else:
+            S["res"] = compute(S)
+        acc.collect(i, S["res"])
+    merge_sharded(*acc.rings(), rank, world, 0.05)
     torch.cuda.synchronize()
     # what the link gives for exactly these buffers (pure copies, nothing else running): the floor of an e2e step
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -794,7 +825,7 @@ def run_e2e(args, stage, feats_h, rois_h, heads_h, heads, feats, rois, dev, worl
     return {"value": steps * args.tiles * world / (ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": ms / steps,
             "h2d_only_ms_per_step": h2d_ms, "h2d_gbs": h2d / h2d_ms / 1e6,
-            "overlap": "H2D of step i+1 and D2H of step i-1 overlap the kernels of step i (two buffer sets, copy streams)"}
+            "host_memory": "write-combined pinned" if args.host_wc else "pinned", "overlap": "H2D of step i+1 and D2H of step i-1 overlap the kernels of step i (two buffer sets, copy streams)"}
 
 
 if __name__ == "__main__":

@@ -62,9 +62,10 @@ class CudaMergeEngine:
             return indeg[:N], in_off, in_list
         raise L.NuhtcError("merge_graph: candidate-pair capacity could not be satisfied")
 
-    def rounds(self, in_off, indeg, in_list, frozen, state, nrounds: int) -> torch.Tensor:
+    def rounds(self, in_off, indeg, in_list, frozen, state, nrounds: int, remaining: Optional[torch.Tensor] = None) -> torch.Tensor:
         dev = state.device
-        remaining = torch.zeros(1, dtype=torch.int64, device=dev)
+        if remaining is None:
+            remaining = torch.zeros(1, dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             rc = L.lib().nuhtc_merge_rounds(in_off.data_ptr(), indeg.data_ptr(), in_list.data_ptr(), state.numel(),
                                             L.ptr(frozen), state.data_ptr(), remaining.data_ptr(), int(nrounds), L.stream_ptr(dev))
@@ -78,6 +79,14 @@ def stripe_extent(shard_meta: Dict, rows: Tuple[int, int]) -> Optional[Tuple[flo
     if r1 <= r0:
         return None
     return float(r0 * shard_meta["stride"]), float((r1 - 1) * shard_meta["stride"] + shard_meta["tile"])
+
+
+def _all_gather_flat(out: torch.Tensor, inp: torch.Tensor, world: int, group) -> None:
+    """out [world * n] <- every rank's inp [n] (one collective; the list form only where the backend lacks the flat one)."""
+    if hasattr(dist, "all_gather_into_tensor") and inp.device.type == "cuda":
+        dist.all_gather_into_tensor(out, inp, group=group)
+    else:
+        dist.all_gather(list(out.view(world, -1).unbind(0)), inp, group=group)
 
 
 def _all_gather_ragged(t: torch.Tensor, counts: List[int], group) -> List[torch.Tensor]:
@@ -233,10 +242,12 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     extents = [stripe_extent(shard, stripe_rows(shard["tiles_y"], q, world)) for q in range(world)]
 
     # ---- band = own nuclei that reach into another rank's stripe
-    band = torch.zeros(N, dtype=torch.bool, device=dev)
-    for q, e in enumerate(extents):
-        if q != rank and e is not None:
-            band |= (ymax >= e[0]) & (ymin <= e[1])
+    others = [e for q, e in enumerate(extents) if q != rank and e is not None]
+    if others and N:
+        E = torch.tensor(others, dtype=torch.float64, device=dev)                   # [world-1, 2]
+        band = ((ymax[:, None] >= E[None, :, 0]) & (ymin[:, None] <= E[None, :, 1])).any(dim=1)
+    else:
+        band = torch.zeros(N, dtype=torch.bool, device=dev)
     bidx = band.nonzero().squeeze(1)
     nb = int(bidx.numel())
     bcnt = cnt[bidx]
@@ -244,30 +255,42 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     bvoff[1:] = torch.cumsum(bcnt, 0)
     nv = int(bvoff[-1].item()) if nb else 0
     if nb:
-        bseg = torch.repeat_interleave(torch.arange(nb, device=dev), bcnt)
+        bseg = torch.repeat_interleave(torch.arange(nb, device=dev), bcnt, output_size=nv)
         src = voff[bidx][bseg] + (torch.arange(nv, device=dev) - bvoff[:-1][bseg])
         bxy = xy[src]
     else:
         bxy = xy[:0]
     mark("band")
-    # ---- one exchange of the band nuclei (counts, then padded records)
+    # ---- one exchange of the band nuclei: the counts, then ONE flat buffer per rank [5 doubles per nucleus | 2 per vertex]
     sizes = torch.tensor([nb, nv], dtype=torch.int64, device=dev)
-    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes, group=group)
-    all_sizes = [s.tolist() for s in all_sizes]
+    all_sizes_t = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    _all_gather_flat(all_sizes_t, sizes, world, group)
+    all_sizes = all_sizes_t.view(world, 2).tolist()
     ncounts = [s[0] for s in all_sizes]
     vcounts = [s[1] for s in all_sizes]
-    meta = torch.stack([score[bidx], gid[bidx].to(torch.float64), bcnt.to(torch.float64), ymin[bidx], ymax[bidx]], dim=1) \
-        if nb else torch.zeros((0, 5), dtype=torch.float64, device=dev)
-    g_meta = _all_gather_ragged(meta, ncounts, group)
-    g_xy = _all_gather_ragged(bxy, vcounts, group)
+    mxn, mxv = max(max(ncounts), 1), max(max(vcounts), 1)
+    rec_len = 5 * mxn + 2 * mxv
+    send = torch.zeros(rec_len, dtype=torch.float64, device=dev)
+    if nb:
+        sm = send[: 5 * nb].view(nb, 5)
+        sm[:, 0] = score[bidx]
+        sm[:, 1] = gid[bidx]
+        sm[:, 2] = bcnt
+        sm[:, 3] = ymin[bidx]
+        sm[:, 4] = ymax[bidx]
+        send[5 * mxn: 5 * mxn + 2 * nv].view(nv, 2).copy_(bxy)
+    recv = torch.empty(world * rec_len, dtype=torch.float64, device=dev)
+    _all_gather_flat(recv, send, world, group)
+    recv = recv.view(world, rec_len)
+    g_meta = [recv[q, : 5 * ncounts[q]].view(ncounts[q], 5) for q in range(world)]
+    g_xy = [recv[q, 5 * mxn: 5 * mxn + 2 * vcounts[q]].view(vcounts[q], 2) for q in range(world)]
 
     mark("exchange")
     # ---- halo = foreign band nuclei that reach into MY stripe (one pass over the concatenated records of all ranks)
     me = extents[rank]
     f_meta = torch.cat(g_meta) if sum(ncounts) else torch.zeros((0, 5), dtype=torch.float64, device=dev)
     f_xy = torch.cat(g_xy) if sum(vcounts) else xy[:0]
-    f_rank = torch.repeat_interleave(torch.arange(world, device=dev), torch.as_tensor(ncounts, device=dev))
+    f_rank = torch.repeat_interleave(torch.arange(world, device=dev), torch.tensor(ncounts, device=dev), output_size=sum(ncounts))
     if me is not None and f_meta.shape[0]:
         take = (f_meta[:, 4] >= me[0]) & (f_meta[:, 3] <= me[1]) & (f_rank != rank)
         halo_flat = take.nonzero().squeeze(1)          # positions in the concatenated band list (rank-major, band order)
@@ -281,7 +304,8 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
         tc = c[halo_flat]
         toff = torch.zeros(H + 1, dtype=torch.int64, device=dev)
         toff[1:] = torch.cumsum(tc, 0)
-        tseg = torch.repeat_interleave(torch.arange(H, device=dev), tc)
+        nhv = int(toff[-1].item())
+        tseg = torch.repeat_interleave(torch.arange(H, device=dev), tc, output_size=nhv)
         vsrc = off[:-1][halo_flat][tseg] + (torch.arange(tseg.numel(), device=dev) - toff[:-1][tseg])
         a_score = torch.cat([score, f_meta[halo_flat, 0]])
         a_gid = torch.cat([gid, f_meta[halo_flat, 1].to(torch.int64)])
@@ -296,17 +320,15 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     p_voff[1:] = torch.cumsum(a_cnt, 0)
     p_xy = a_xy.contiguous()
     p_score = a_score.contiguous()
-    inv = torch.arange(M, device=dev)                # position of local-set element i (kept for the index algebra below)
 
     mark("halo+permute")
     indeg, in_off, in_list = engine.graph(p_xy, p_voff, p_score, overlap_threshold)
     mark("graph")
     frozen = torch.zeros(M, dtype=torch.uint8, device=dev)
-    frozen[inv[N:]] = 1
-    state = torch.where((indeg[:M] == 0) & (frozen == 0), 1, 0).to(torch.uint8)
-    own_pos = inv[:N]
-    band_pos = own_pos[bidx]
-    halo_pos = inv[N:]
+    frozen[N:] = 1                                   # halo copies: read, never written (their owners decide)
+    state = (indeg[:M] == 0).to(torch.uint8)
+    state[N:] = 0
+    band_pos = bidx
 
     # ---- resolve: sweep own nuclei, exchange band states, until nobody has an undecided own nucleus.  ONE collective per
     # iteration: every rank appends its count of undecided own nuclei (8 bytes) to its band states, so the termination test
@@ -314,9 +336,13 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     # the slowest host holds everybody up).
     # Every rank sends one fixed-size message: [undecided own nuclei (int64) | band states | padding]; the halo copies
     # read their owners' states straight out of the gathered buffer through an index computed once.
-    mx = 8 + max(max(ncounts), 1)
+    mx = 8 * ((8 + max(max(ncounts), 1) + 7) // 8)
     msg = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    msg_remaining = msg[:8].view(torch.int64)              # the rounds kernel writes its counter straight into the message
+    msg_band = msg[8:8 + nb]
     gathered = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+    g_remaining = gathered.view(world, mx)[:, :8]
+    state_halo = state[N:]
     if H:
         starts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
         starts[1:] = torch.cumsum(torch.as_tensor(ncounts, device=dev), 0)
@@ -324,34 +350,32 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
         halo_src = hr * mx + 8 + (halo_flat - starts[hr])      # position of each halo nucleus' state in `gathered`
     blind = 2          # iterations between two looks at the termination counter: the host only waits once per `blind` exchanges
     done = False
+    iters = 0
     for _ in range(1 << 18):
-        tots = []
         for _k in range(blind):
-            remaining = engine.rounds(in_off, indeg, in_list, frozen, state, 8)
-            msg[:8] = remaining.reshape(1).to(torch.int64).view(torch.uint8)
+            # the first call settles the interior (dependency chains inside a crowded tile overlap run a few dozen deep);
+            # afterwards only what hangs on halo states is left
+            engine.rounds(in_off, indeg, in_list, frozen, state, 32 if iters == 0 else 8, msg_remaining)
             if nb:
-                msg[8:8 + nb] = state[band_pos]
-            if hasattr(dist, "all_gather_into_tensor") and dev.type == "cuda":
-                dist.all_gather_into_tensor(gathered, msg, group=group)
-            else:
-                dist.all_gather(list(gathered.view(world, mx).unbind(0)), msg, group=group)
-            tots.append(gathered.view(world, mx)[:, :8].contiguous().view(torch.int64).sum())
+                torch.index_select(state, 0, band_pos, out=msg_band)
+            _all_gather_flat(gathered, msg, world, group)
             if H:
-                state[halo_pos] = gathered[halo_src]
-        # an iteration that found nothing undecided anywhere leaves every later one a no-op, so any zero ends the loop
-        if int(torch.stack(tots).min().item()) == 0:
+                torch.index_select(gathered, 0, halo_src, out=state_halo)
+            iters += 1
+        # an iteration that found nothing undecided anywhere leaves every later one a no-op, so looking at the last one is enough
+        if int(g_remaining.contiguous().view(torch.int64).sum().item()) == 0:
             done = True
             break
     assert done
     mark("resolve")
     if trace:
         print("seam trace (ms):", ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])),
-              f"| own {N} band {nb} halo {H}", flush=True)
+              f"| own {N} band {nb} halo {H} resolve iterations {iters}", flush=True)
     if merge_strategy == "area":
         flagged = _area_picks(xy, voff, score, gid, a_score, a_gid, state, indeg, in_off, in_list, bidx, ncounts, rank, group)
         mark("area picks")
     else:
-        flagged = state[own_pos] == 1
+        flagged = state[:N] == 1
     kept_local = flagged.nonzero().squeeze(1)
     order = torch.argsort(-score[kept_local], stable=True)
     kept_local = kept_local[order]

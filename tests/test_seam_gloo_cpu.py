@@ -42,7 +42,7 @@ class OracleEngine:
         in_list = torch.tensor([a for x in ins for a in x] + [0], dtype=torch.int32)
         return indeg, in_off, in_list
 
-    def rounds(self, in_off, indeg, in_list, frozen, state, nrounds):
+    def rounds(self, in_off, indeg, in_list, frozen, state, nrounds, remaining=None):
         rem = 0
         for _ in range(nrounds):
             rem = 0
@@ -58,6 +58,9 @@ class OracleEngine:
                     state[i] = 1
                 else:
                     rem += 1
+        if remaining is not None:
+            remaining.fill_(rem)
+            return remaining
         return torch.tensor([rem], dtype=torch.int64)
 
 
