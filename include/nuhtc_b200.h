@@ -272,6 +272,25 @@ int nuhtc_tile_filter(const float *det_boxes, const int32_t *area, const int32_t
 int nuhtc_keep_flags(const int32_t *keep, const int32_t *tile_start, const int32_t *tile_count, int num_tiles,
                      int max_tile_size, int64_t n, uint8_t *flags, void *stream);
 
+/* ---- RPN proposal pre-selection ---------------------------------------------------
+ * Replaces the per-level body of `RPNHead._get_bboxes_single` (mmdet/models/dense_heads/rpn_head.py:103-165:
+ * permute, sigmoid, `scores.sort(descending=True)`, `[:nms_pre]`, index gathers) and the decode + min-size
+ * test of `_bbox_post_process` (:167-236) for a whole batch in ONE launch.
+ *   cls[l] [B,A,H_l,W_l] logits, reg[l] [B,4A,H_l,W_l], anchors[l] [H_l*W_l*A,4] in (h,w,a) order (device, fp32).
+ *   Per image the output holds, level after level, k_l = min(nms_pre, n_l) candidates (nms_pre <= 0: all): the
+ *   nms_pre best scores of the level in descending order, ties by ascending anchor index (levels with
+ *   n_l <= nms_pre keep their natural order, as the reference does not sort them):
+ *   boxes [B,sum k_l,4] decoded with means 0 / stds 1 and clamped to (max_h,max_w) when both > 0, scores
+ *   (sigmoid applied when apply_sigmoid), labels [..] int64 = level, groups [..] int32 = image index, or -1
+ *   when w or h <= min_bbox_size (min_bbox_size < 0: no test) -- the arrays nuhtc_nms reads.
+ * nuhtc_rpn_topk_supported: 1 if every level that needs a selection fits the shared-memory select
+ *   (H*W*A*4 + 24.3 KB <= 227 KB, nms_pre <= 2048); otherwise the caller uses a sort-based path. */
+int nuhtc_rpn_topk_supported(const int *H, const int *W, int L, int A, int nms_pre);
+int nuhtc_rpn_topk_decode(const float *const *cls, const float *const *reg, const float *const *anchors, const int *H,
+                          const int *W, int L, int B, int A, int nms_pre, int apply_sigmoid, int max_h, int max_w,
+                          double wh_ratio_clip, float min_bbox_size, float *boxes, float *scores, int64_t *labels,
+                          int32_t *groups, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,12 +7,9 @@
 // Every arithmetic step is a separately rounded fp32 operation (__fmul_rn / __fadd_rn), exactly what the chain of torch
 // kernels computes; expf is the same libdevice routine ATen's exp kernel calls.
 #include "common.cuh"
+#include "decode.cuh"
 
 namespace {
-
-struct F4 {
-    float v[4];
-};
 
 __global__ void delta2bbox_kernel(const float *__restrict__ rois, int with_batch, const float *__restrict__ deltas, int64_t K,
                                   F4 means, F4 stds, float max_ratio, int clamp, float max_w, float max_h, float inv_scale_div,
@@ -23,26 +20,9 @@ __global__ void delta2bbox_kernel(const float *__restrict__ rois, int with_batch
     const float *r = rois + k * rs + (with_batch ? 1 : 0);
     const float4 dl = *reinterpret_cast<const float4 *>(deltas + k * 4);
     const float x1 = r[0], y1 = r[1], x2 = r[2], y2 = r[3];
-    const float dx = __fadd_rn(__fmul_rn(dl.x, stds.v[0]), means.v[0]);
-    const float dy = __fadd_rn(__fmul_rn(dl.y, stds.v[1]), means.v[1]);
-    float dw = __fadd_rn(__fmul_rn(dl.z, stds.v[2]), means.v[2]);
-    float dh = __fadd_rn(__fmul_rn(dl.w, stds.v[3]), means.v[3]);
-    const float px = __fmul_rn(__fadd_rn(x1, x2), 0.5f), py = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
-    const float pw = __fsub_rn(x2, x1), ph = __fsub_rn(y2, y1);
-    const float sx = __fmul_rn(pw, dx), sy = __fmul_rn(ph, dy);
-    // torch.clamp propagates NaN; fminf/fmaxf would not
-    dw = dw != dw ? dw : fminf(fmaxf(dw, -max_ratio), max_ratio);
-    dh = dh != dh ? dh : fminf(fmaxf(dh, -max_ratio), max_ratio);
-    const float gx = __fadd_rn(px, sx), gy = __fadd_rn(py, sy);
-    const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh));
-    const float hw = __fmul_rn(gw, 0.5f), hh = __fmul_rn(gh, 0.5f);
-    float o0 = __fsub_rn(gx, hw), o1 = __fsub_rn(gy, hh), o2 = __fadd_rn(gx, hw), o3 = __fadd_rn(gy, hh);
-    if (clamp) {
-        o0 = o0 != o0 ? o0 : fminf(fmaxf(o0, 0.f), max_w);
-        o2 = o2 != o2 ? o2 : fminf(fmaxf(o2, 0.f), max_w);
-        o1 = o1 != o1 ? o1 : fminf(fmaxf(o1, 0.f), max_h);
-        o3 = o3 != o3 ? o3 : fminf(fmaxf(o3, 0.f), max_h);
-    }
+    float o4[4];
+    decode_box(x1, y1, x2, y2, dl, means, stds, max_ratio, clamp, max_w, max_h, o4);
+    float o0 = o4[0], o1 = o4[1], o2 = o4[2], o3 = o4[3];
     if (divide) {
         o0 = __fdiv_rn(o0, inv_scale_div);
         o1 = __fdiv_rn(o1, inv_scale_div);

@@ -84,3 +84,53 @@ def test_single_and_batched_vs_oracle(oracle, nms_pre, min_size):
                                             dict(type="nms", iou_threshold=0.7), 400, min_size)
         if full.shape == ref.shape:
             assert (full - ref).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("nms_pre,quant,min_size", [(1000, 0.0, 0), (2000, 0.0, -1), (1000, 0.25, 6), (100000, 0.0, 0)])
+def test_fused_topk_decode_equals_sort_path(nms_pre, quant, min_size):
+    """nuhtc_rpn_topk_decode (shared-memory radix select + bitonic sort + decode, one launch) against torch's sigmoid + stable
+    sort + gathers + the delta2bbox kernel: every array the NMS reads must be bit-identical, ties included (quantised logits
+    give thousands of equal scores; the k-th score then is a tie that must be cut by ascending anchor index)."""
+    from nuhtc_b200 import rpn
+    from nuhtc_b200.roi_stage import delta2bbox
+    B = 4
+    cls, reg, anchors = _levels(B, seed=5)
+    if quant:
+        cls = [torch.round(c / quant) * quant for c in cls]
+    gc, gr, ga = [x.cuda() for x in cls], [x.cuda() for x in reg], [x.cuda() for x in anchors]
+    fused = rpn._topk_decode(gc, gr, ga, (512, 512, 3), nms_pre, min_size, True, "auto")
+    assert fused is not None
+    boxes, scores, labels, groups, per_image, per_level = fused
+    boxes, scores, labels, groups = boxes.view(B, per_image, 4), scores.view(B, per_image), labels.view(B, per_image), groups.view(B, per_image)
+    for b in range(B):
+        off = 0
+        for l in range(4):
+            s = gc[l][b].permute(1, 2, 0).reshape(-1).sigmoid()
+            d = gr[l][b].permute(1, 2, 0).reshape(-1, 4)
+            a = ga[l]
+            if 0 < nms_pre < s.numel():
+                rs, ri = s.sort(descending=True, stable=True)
+                s, d, a = rs[:nms_pre], d[ri[:nms_pre]], a[ri[:nms_pre]]
+            k = s.numel()
+            ref_boxes = delta2bbox(a.contiguous(), d.contiguous(), (1., 1., 1., 1.), max_shape=(512, 512, 3))
+            assert torch.equal(scores[b, off:off + k], s), (b, l)
+            assert torch.equal(boxes[b, off:off + k], ref_boxes), (b, l)
+            assert (labels[b, off:off + k] == l).all()
+            ok = torch.ones(k, dtype=torch.bool, device="cuda")
+            if min_size >= 0:
+                ok = ((ref_boxes[:, 2] - ref_boxes[:, 0]) > min_size) & ((ref_boxes[:, 3] - ref_boxes[:, 1]) > min_size)
+            assert torch.equal(groups[b, off:off + k], torch.where(ok, b, -1).to(torch.int32))
+            off += k
+        assert off == per_image
+
+
+def test_batched_fused_equals_sort_impl():
+    from nuhtc_b200 import rpn
+    cls, reg, anchors = _levels(16, seed=3)
+    cfg = Cfg(nms_pre=1000, min_bbox_size=0, nms=dict(type="nms", iou_threshold=0.7), max_per_img=1000)
+    gc, gr, ga = [x.cuda() for x in cls], [x.cuda() for x in reg], [x.cuda() for x in anchors]
+    a = rpn.proposals_batched(gc, gr, ga, (512, 512, 3), cfg, impl="auto")
+    b = rpn.proposals_batched(gc, gr, ga, (512, 512, 3), cfg, impl="sort")
+    assert len(a) == len(b) == 16
+    for x, y in zip(a, b):
+        assert x.shape[0] > 100 and torch.equal(x, y)
