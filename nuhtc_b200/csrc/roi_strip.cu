@@ -800,8 +800,7 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
     auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TEAM) : "memory"); };
     // tile write: the four channels of a thread are written in an order rotated by q/2 (784*q = 16*q mod 32: without the
     // rotation the quads of a phase would pile onto two bank groups)
-    const int rot = (q >> 1) & 3;
-    const bool r1 = rot & 1, r2 = rot & 2;
+    const bool r2 = (q & 2) != 0;   // quads 2,3 of a flush phase (see the flush)
     unsigned rec_uses[2] = {0u, 0u};
     bool store_pending = false;
 
@@ -937,37 +936,46 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
                     }
                 }
             }
-            // ---- flush: two 16-channel phases through the team tile
+            // ---- flush: two 16-channel phases through the team tile.  Only the 16 lanes of a warp whose quads belong to the
+            // phase store; their channel rows sit 16 banks apart for neighbouring quads (196 floats = 4 banks per channel), so
+            // quads 2,3 of a phase store their channel pairs in swapped order -- a rotation by two, which is a register
+            // renaming of (acc[.][0], acc[.][1]), not a per-value select chain -- and the 16 lanes hit 16 different banks.
             float *outp = a.out + ((size_t)k * a.C + (size_t)cg * kCG) * PP;
+            auto flush = [&](auto HASBIAS) {
+                constexpr bool kBias = decltype(HASBIAS)::value;
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                if (tt == 0 && store_pending) tma_store_wait_read();
-                team_sync();
-                if (worker && (q >> 2) == f && !(a.dbg & 2)) {
-                    const int cl = 4 * (q & 3);
-                    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (a.bias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 4 * q);
+                for (int f = 0; f < 2; ++f) {
+                    if (tt == 0 && store_pending) tma_store_wait_read();
+                    team_sync();
+                    if (worker && (q >> 2) == f && !(a.dbg & 2)) {
+                        const int cl = 4 * (q & 3);
+                        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (kBias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 4 * q);
+                        float *tp = tile + pw;
+                        float *tlo = tp + (cl + (r2 ? 2 : 0)) * PP, *thi = tp + (cl + (r2 ? 0 : 2)) * PP;
 #pragma unroll
-                    for (int i = 0; i < P; ++i) {
-                        float a0 = acc[i][0].x, a1 = acc[i][0].y, a2 = acc[i][1].x, a3 = acc[i][1].y;
-                        if (a.bias) {
-                            a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
+                        for (int i = 0; i < P; ++i) {
+                            float a0 = acc[i][0].x, a1 = acc[i][0].y, a2 = acc[i][1].x, a3 = acc[i][1].y;
+                            if (kBias) {
+                                a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
+                            }
+                            // first instruction pair: channels cl+0,1 for quads 0,1 of the phase, cl+2,3 for quads 2,3
+                            tlo[i * P] = r2 ? a2 : a0;
+                            tlo[i * P + PP] = r2 ? a3 : a1;
+                            thi[i * P] = r2 ? a0 : a2;
+                            thi[i * P + PP] = r2 ? a1 : a3;
                         }
-                        float *tp = tile + i * P + pw;
-                        const float b0 = r2 ? a2 : a0, b1 = r2 ? a3 : a1, b2 = r2 ? a0 : a2, b3 = r2 ? a1 : a3;
-                        tp[(cl + ((0 + rot) & 3)) * PP] = r1 ? b1 : b0;
-                        tp[(cl + ((1 + rot) & 3)) * PP] = r1 ? b2 : b1;
-                        tp[(cl + ((2 + rot) & 3)) * PP] = r1 ? b3 : b2;
-                        tp[(cl + ((3 + rot) & 3)) * PP] = r1 ? b0 : b3;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    team_sync();
+                    if (tt == 0) {
+                        tma_bulk_s2g(outp + (size_t)f * Cfg::TILE_FLOATS, smem_u32(tile), Cfg::TILE_FLOATS * 4);
+                        store_pending = true;
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                team_sync();
-                if (tt == 0) {
-                    tma_bulk_s2g(outp + (size_t)f * Cfg::TILE_FLOATS, smem_u32(tile), Cfg::TILE_FLOATS * 4);
-                    store_pending = true;
-                }
-            }
+            };
+            if (a.bias) flush(std::true_type{});
+            else flush(std::false_type{});
             ++it;
             cur = s_pop[team * 2 + (it & 1)];   // written before the team barriers of the flush
             curbuf ^= 1;
