@@ -291,6 +291,21 @@ int nuhtc_rpn_topk_decode(const float *const *cls, const float *const *reg, cons
                           double wh_ratio_clip, float min_bbox_size, float *boxes, float *scores, int64_t *labels,
                           int32_t *groups, void *stream);
 
+/* ---- watershed proposals: instances of a semantic mask -----------------------------
+ * Replaces the host tail of `HybridTaskCascadeRoIHead_Cus._watershed_proposal`
+ * (nuhtc/models/htc_roi_head_cus.py:303-335: per image a device->host copy, ndi.binary_fill_holes,
+ * ndi.distance_transform_edt, ndi.label(distance > 0.25), skimage watershed(-distance, markers, mask), a
+ * relabel loop, a one-hot [n,H,W] tensor, areas and the `_inst_mask_to_bbox` loop :263-281).  With the
+ * Euclidean distance as the landscape every mask pixel is a marker (distance >= 1 > 0.25), so the instances
+ * are the 4-connected components of the hole-filled mask in raster order of their first pixel.
+ *   mask [B,H,W] fp32 (0 = background, anything else = foreground; the reference's mask after binary_open).
+ *   boxes [B,max_boxes,5] fp32 out: (x0, y0, x1+1, y1+1, 1.0) of the components with
+ *   min_area < area < max_area, in label order; counts [B] int32 out: how many qualified (a count above
+ *   max_boxes means the tail was dropped).  filled [B,H,W] uint8 out or NULL: the hole-filled mask. */
+size_t nuhtc_mask_components_workspace_bytes(int B, int H, int W);
+int nuhtc_mask_components(const float *mask, int B, int H, int W, int min_area, int max_area, int max_boxes,
+                          float *boxes, int32_t *counts, uint8_t *filled, void *ws, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

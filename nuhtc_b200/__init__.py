@@ -12,6 +12,6 @@ from .mask_paste import _do_paste_mask, paste_masks, get_seg_masks, get_seg_mask
 from .mask_nms import mask_nms, mask_nms_device, pack_masks
 from .nuclei_merge import merge_arrays, merge_overlap
 from .contours import mask_contours, mask2inst, rings_for_merge
-from . import slide, synth, roi_stage, rpn, contours
+from . import slide, synth, roi_stage, rpn, contours, watershed
 
 __version__ = "0.1.0"

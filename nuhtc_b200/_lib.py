@@ -56,6 +56,8 @@ SIGNATURES = {
     "nuhtc_tile_filter": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "nuhtc_rpn_topk_supported": (_i, [_vp, _vp, _i, _i, _i]),
     "nuhtc_rpn_topk_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp, _vp]),
+    "nuhtc_mask_components_workspace_bytes": (_c.c_size_t, [_i, _i, _i]),
+    "nuhtc_mask_components": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _c.c_size_t, _vp]),
     "nuhtc_keep_flags": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp]),
 }
 
@@ -105,7 +107,7 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
 # ---- launch accounting: how many of OUR kernels each C-ABI call enqueues (bench.py reports the sum as
 # "gpu_launches"; library kernels such as cub's radix sort are not counted)
 LAUNCHES = {"n": 0}
-KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "to_cg32": 1, "roi_align_strip": 5, "attention_pool": 4, "roi_align": 1, "nms": 9, "paste": 2, "paste_dual": 1, "pack": 3, "mask_nms": 8, "merge": 16, "contours": 2, "rings": 1, "glue": 1, "rpn_topk": 1}
+KERNELS_PER_CALL = {"nchw_to_nhwc": 1, "to_cg32": 1, "roi_align_strip": 5, "attention_pool": 4, "roi_align": 1, "nms": 9, "paste": 2, "paste_dual": 1, "pack": 3, "mask_nms": 8, "merge": 16, "contours": 2, "rings": 1, "glue": 1, "rpn_topk": 1, "components": 8}
 
 
 def count(op: str, n: int = 1) -> None:

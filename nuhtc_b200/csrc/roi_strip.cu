@@ -694,35 +694,40 @@ __global__ void __launch_bounds__(Strip7Cfg::NTHREADS, 1) roi_align_strip7_kerne
             passed = max(passed, y0 + rel);
             // ---- flush: two 16-channel slices through the warp's tile, one asynchronous bulk store each
             float *outp = a.out + ((size_t)k * a.C + (size_t)cg * kCG) * PP;
+            auto flush = [&](auto HASBIAS) {
+                constexpr bool kBias = decltype(HASBIAS)::value;
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                if (lane == 0 && store_pending) tma_store_wait_read();   // the previous store has read the tile
-                __syncwarp();
-                if (worker && !(a.dbg & 2)) {
-                    const bool hi = odd != (f == 1);   // slice f sits in register set f ^ odd
-                    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (a.bias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 16 * f + 4 * q);
-                    float *tp = tile + (4 * q) * PP + pw;
+                for (int f = 0; f < 2; ++f) {
+                    if (lane == 0 && store_pending) tma_store_wait_read();   // the previous store has read the tile
+                    __syncwarp();
+                    if (worker && !(a.dbg & 2)) {
+                        const bool hi = odd != (f == 1);   // slice f sits in register set f ^ odd
+                        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (kBias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 16 * f + 4 * q);
+                        float *tp = tile + (4 * q) * PP + pw;
 #pragma unroll
-                    for (int i = 0; i < P; ++i) {
-                        float a0 = hi ? acc[1][i][0].x : acc[0][i][0].x, a1 = hi ? acc[1][i][0].y : acc[0][i][0].y;
-                        float a2 = hi ? acc[1][i][1].x : acc[0][i][1].x, a3 = hi ? acc[1][i][1].y : acc[0][i][1].y;
-                        if (a.bias) {
-                            a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
+                        for (int i = 0; i < P; ++i) {
+                            float a0 = hi ? acc[1][i][0].x : acc[0][i][0].x, a1 = hi ? acc[1][i][0].y : acc[0][i][0].y;
+                            float a2 = hi ? acc[1][i][1].x : acc[0][i][1].x, a3 = hi ? acc[1][i][1].y : acc[0][i][1].y;
+                            if (kBias) {
+                                a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
+                            }
+                            tp[i * P] = a0;
+                            tp[i * P + PP] = a1;
+                            tp[i * P + 2 * PP] = a2;
+                            tp[i * P + 3 * PP] = a3;
                         }
-                        tp[i * P] = a0;
-                        tp[i * P + PP] = a1;
-                        tp[i * P + 2 * PP] = a2;
-                        tp[i * P + 3 * PP] = a3;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_bulk_s2g(outp + (size_t)f * Cfg::TILE_FLOATS, smem_u32(tile), Cfg::TILE_FLOATS * 4);
+                        store_pending = true;
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    tma_bulk_s2g(outp + (size_t)f * Cfg::TILE_FLOATS, smem_u32(tile), Cfg::TILE_FLOATS * 4);
-                    store_pending = true;
-                }
-            }
+            };
+            if (a.bias) flush(std::true_type{});
+            else flush(std::false_type{});
             cur = nxt;
             curbuf ^= 1;
         }

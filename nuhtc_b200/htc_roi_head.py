@@ -54,13 +54,15 @@ class HybridTaskCascadeRoIHead_Lite:
                  thres: float = 0.0, finest_scale: float = 56.0, bbox_roi_layer: Optional[dict] = None,
                  mask_roi_layer: Optional[dict] = None, semantic_head: Optional[Callable] = None,
                  semantic_fusion: Sequence[str] = ("bbox", "mask"), semantic_roi_layer: Optional[dict] = None,
-                 semantic_stride: int = 4, watershed_proposal: Optional[Callable] = None, mask_classes: Optional[int] = None):
+                 semantic_stride: int = 4, watershed_proposal=None, mask_classes: Optional[int] = None):
         """Config keys follow configs/nuhtc/htc_lite_swin_pytorch_fpn_PanNuke_seasaw_CAS.py:72-164.
         extractor: 'attention' (AttentionRoIExtractor, start_level / thres) or 'single' (SingleRoIExtractor, finest_scale).
         *_roi_layer: dict(type='RoIAlign', output_size=.., sampling_ratio=..).
         test_cfg: dict(score_thr, nms=dict(type='nms', iou_threshold=..), max_per_img, mask_thr_binary).
-        watershed_proposal: the reference adds watershed proposals on the host (scipy / skimage, htc_roi_head_cus.py:283-342);
-        pass a callable (semantic_pred, proposal_list, img_shape) -> proposal_list to keep that step, None skips it."""
+        watershed_proposal: True = prepend the watershed proposals of the semantic prediction to every image's proposals
+        (`with_watershed_proposal`, htc_roi_head_cus.py:2217-2221; needs a semantic_head) with nuhtc_b200.watershed (device
+        resident; the reference does this step on the host with scipy / skimage); a callable
+        (semantic_pred, proposal_list, img_shape) -> proposal_list replaces it; None / False skips it."""
         assert len(bbox_head) == num_stages
         bl = dict(bbox_roi_layer or dict(type="RoIAlign", output_size=7, sampling_ratio=2))
         ml = dict(mask_roi_layer or dict(type="RoIAlign", output_size=14, sampling_ratio=0))
@@ -76,7 +78,12 @@ class HybridTaskCascadeRoIHead_Lite:
         self.semantic_head = semantic_head
         self.with_semantic = semantic_head is not None
         self.semantic_fusion = tuple(semantic_fusion) if self.with_semantic else ()
-        self.watershed_proposal = watershed_proposal
+        if watershed_proposal is True:
+            from .watershed import watershed_proposal as _ws
+
+            def watershed_proposal(semantic_pred, proposal_list, img_shape):
+                return _ws(semantic_pred, proposal_list=proposal_list, img_shape=img_shape, min_area=10, thres=0)[0]
+        self.watershed_proposal = watershed_proposal or None
         self.test_cfg = dict(test_cfg)
         self.num_classes = int(getattr(self.bbox_head[-1], "num_classes"))
         self.mask_classes = int(mask_classes if mask_classes is not None else self.num_classes)

@@ -491,3 +491,64 @@ def drop_threshold_ties(d: dict, overlap_threshold: float, max_rounds: int = 8):
             lo = a if sub["score"][a] < sub["score"][b] else b
             alive[idx[lo]] = False
     raise RuntimeError("threshold ties remain")
+
+
+# --------------------------------------------------------------------------- watershed proposals
+def gaussian_blur5(x: torch.Tensor) -> torch.Tensor:
+    """torchvision TF.gaussian_blur(x, kernel_size=5), sigma=None -> 0.3*((5-1)*0.5-1)+0.8 = 1.1, reflect padding
+    (torchvision/transforms/_functional_tensor.py: _get_gaussian_kernel2d, gaussian_blur)."""
+    sigma = 0.3 * ((5 - 1) * 0.5 - 1) + 0.8
+    g = torch.linspace(-2.0, 2.0, steps=5, dtype=x.dtype)
+    pdf = torch.exp(-0.5 * (g / sigma).pow(2))
+    k1 = pdf / pdf.sum()
+    k2 = torch.mm(k1[:, None], k1[None, :]).expand(x.shape[1], 1, 5, 5)
+    return F.conv2d(F.pad(x, [2, 2, 2, 2], mode="reflect"), k2, groups=x.shape[1])
+
+
+def watershed_semantic_mask(semantic_pred: torch.Tensor, img_shape, thres: float = 0.0) -> torch.Tensor:
+    """First (device) half of _watershed_proposal, nuhtc/models/htc_roi_head_cus.py:285-299 -> [B,H,W] float 0/1."""
+    m = F.interpolate(semantic_pred, size=tuple(int(v) for v in img_shape[:2]), mode="bilinear", align_corners=True)
+    m = gaussian_blur5(m)
+    m = (m > thres).to(semantic_pred.dtype)
+    k = torch.ones((1, 1, 5, 5), dtype=m.dtype)
+    for _ in range(2):
+        m = torch.clamp(F.conv2d(m, k, padding=2) - k.sum() + 1, min=0, max=1)
+    for _ in range(2):
+        m = torch.clamp(F.conv2d(m, k, padding=2), min=0, max=1)
+    return m[:, 0]
+
+
+def watershed_instances(mask: np.ndarray, min_area: int = 10):
+    """Second (host) half, htc_roi_head_cus.py:303-335, for ONE image: binary_fill_holes, EDT, label(distance > 0.25),
+    watershed, area filter, _inst_mask_to_bbox (:263-281) -> (boxes [n,5] float32, filled mask).
+
+    skimage is not in this image.  `watershed(-distance, markers, mask=mask)` floods from the markers over the mask; here the
+    markers cover the whole mask (checked below: the Euclidean distance of a foreground pixel is >= 1 > 0.25), so there is
+    nothing left to flood and it returns the markers."""
+    from scipy import ndimage as ndi
+    filled = ndi.binary_fill_holes(mask.astype(bool))
+    distance = ndi.distance_transform_edt(filled)
+    dist_mask = distance > 0.25
+    assert (dist_mask == filled).all()
+    markers, n = ndi.label(dist_mask)
+    inst = markers
+    max_area = mask.shape[0] * mask.shape[1] / 4
+    boxes = []
+    for lab in range(1, n + 1):
+        ys, xs = np.nonzero(inst == lab)
+        area = ys.size
+        if area > min_area and area < max_area:
+            boxes.append([xs.min(), ys.min(), xs.max() + 1, ys.max() + 1, 1.0])
+    return np.asarray(boxes, dtype=np.float32).reshape(-1, 5), filled
+
+
+def watershed_proposal(semantic_pred: torch.Tensor, proposal_list=None, img_shape=None, min_area: int = 10, thres: float = 0.0):
+    """_watershed_proposal(semantic_pred, proposal_list=..., img_shape=..., min_area, thres) with semantic_dist / sample_num None."""
+    m = watershed_semantic_mask(semantic_pred, img_shape, thres).numpy()
+    ws = [torch.from_numpy(watershed_instances(m[i], min_area)[0]) for i in range(m.shape[0])]
+    if proposal_list is not None:
+        proposal_list = list(proposal_list)
+        for i, w in enumerate(ws):
+            if len(w):
+                proposal_list[i] = torch.cat((w, proposal_list[i]), dim=0)
+    return proposal_list, ws
