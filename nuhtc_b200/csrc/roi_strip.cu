@@ -752,7 +752,7 @@ static size_t strip7_smem_bytes() {
 struct Strip14Cfg {
     static constexpr int NT = 3, TW = 4, TEAM = TW * 32;
     static constexpr int NTHREADS = 32 + NT * TEAM;
-    static constexpr int TILE_FLOATS = 16 * 196;
+    static constexpr int TILE_FLOATS = 32 * 196;      // the whole [32][14][14] result of a record: ONE bulk store
     static constexpr int FIXED = NT * (TILE_FLOATS * 4 + 2 * (int)sizeof(StripRec<14>)) + kNU * (int)sizeof(UnitSlot) + 64 * NT + 16 * kNU + 256;
     static constexpr int NR_RAW = (kSmemMax - FIXED) / (kRowFloats * 4 + 16);
     static constexpr int NR = NR_RAW > 32 ? 32 : NR_RAW;
@@ -941,42 +941,40 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
                     }
                 }
             }
-            // ---- flush: two 16-channel phases through the team tile.  Only the 16 lanes of a warp whose quads belong to the
-            // phase store; their channel rows sit 16 banks apart for neighbouring quads (196 floats = 4 banks per channel), so
-            // quads 2,3 of a phase store their channel pairs in swapped order -- a rotation by two, which is a register
-            // renaming of (acc[.][0], acc[.][1]), not a per-value select chain -- and the 16 lanes hit 16 different banks.
+            // ---- flush: the [32][196] result through the team tile, one pass, one bulk store.  A channel row is 196 floats =
+            // 4 banks, so the 8 quads of an output column sit 16 banks apart: quads 2,3 (mod 4) store their channel pairs in
+            // swapped order (a rotation by two = a renaming of acc[.][0] / acc[.][1], one select per value), which leaves quad q
+            // and q + 4 on the same bank -- a 2-way conflict, i.e. as many wavefronts as two half-warp passes would take at
+            // half the issue slots (every warp holds quads of both halves, so a split pass is issued twice by every warp).
             float *outp = a.out + ((size_t)k * a.C + (size_t)cg * kCG) * PP;
             auto flush = [&](auto HASBIAS) {
                 constexpr bool kBias = decltype(HASBIAS)::value;
+                if (tt == 0 && store_pending) tma_store_wait_read();
+                team_sync();
+                if (worker && !(a.dbg & 2)) {
+                    const int cl = 4 * q;
+                    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kBias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 4 * q);
+                    float *tp = tile + pw;
+                    float *tlo = tp + (cl + (r2 ? 2 : 0)) * PP, *thi = tp + (cl + (r2 ? 0 : 2)) * PP;
 #pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    if (tt == 0 && store_pending) tma_store_wait_read();
-                    team_sync();
-                    if (worker && (q >> 2) == f && !(a.dbg & 2)) {
-                        const int cl = 4 * (q & 3);
-                        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (kBias) bz = ldg_f4(a.bias + (size_t)k * a.C + cg * kCG + 4 * q);
-                        float *tp = tile + pw;
-                        float *tlo = tp + (cl + (r2 ? 2 : 0)) * PP, *thi = tp + (cl + (r2 ? 0 : 2)) * PP;
-#pragma unroll
-                        for (int i = 0; i < P; ++i) {
-                            float a0 = acc[i][0].x, a1 = acc[i][0].y, a2 = acc[i][1].x, a3 = acc[i][1].y;
-                            if (kBias) {
-                                a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
-                            }
-                            // first instruction pair: channels cl+0,1 for quads 0,1 of the phase, cl+2,3 for quads 2,3
-                            tlo[i * P] = r2 ? a2 : a0;
-                            tlo[i * P + PP] = r2 ? a3 : a1;
-                            thi[i * P] = r2 ? a0 : a2;
-                            thi[i * P + PP] = r2 ? a1 : a3;
+                    for (int i = 0; i < P; ++i) {
+                        float a0 = acc[i][0].x, a1 = acc[i][0].y, a2 = acc[i][1].x, a3 = acc[i][1].y;
+                        if (kBias) {
+                            a0 += bz.x; a1 += bz.y; a2 += bz.z; a3 += bz.w;
                         }
+                        // first instruction pair: channels cl+0,1 for quads 0,1 (mod 4), cl+2,3 for quads 2,3
+                        tlo[i * P] = r2 ? a2 : a0;
+                        tlo[i * P + PP] = r2 ? a3 : a1;
+                        thi[i * P] = r2 ? a0 : a2;
+                        thi[i * P + PP] = r2 ? a1 : a3;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    team_sync();
-                    if (tt == 0) {
-                        tma_bulk_s2g(outp + (size_t)f * Cfg::TILE_FLOATS, smem_u32(tile), Cfg::TILE_FLOATS * 4);
-                        store_pending = true;
-                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                team_sync();
+                if (tt == 0) {
+                    tma_bulk_s2g(outp, smem_u32(tile), Cfg::TILE_FLOATS * 4);
+                    store_pending = true;
                 }
             };
             if (a.bias) flush(std::true_type{});
