@@ -2,7 +2,7 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` may import this module.  The product
-package ``nuhtc_b200`` never does (tests/test_no_oracle_in_product.py checks).
+package ``nuhtc_b200`` never does (tests/test_abi_cpu.py::test_product_never_imports_the_oracle checks).
 
 Each function restates one piece of the reference path and cites it.  The
 native arithmetic is in ``nuhtc_oracle.c`` (see its header for the parity
