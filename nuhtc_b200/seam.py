@@ -348,14 +348,14 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
         starts[1:] = torch.cumsum(torch.as_tensor(ncounts, device=dev), 0)
         hr = f_rank[halo_flat]
         halo_src = hr * mx + 8 + (halo_flat - starts[hr])      # position of each halo nucleus' state in `gathered`
-    blind = 2          # iterations between two looks at the termination counter: the host only waits once per `blind` exchanges
+    blind = 3          # iterations between two looks at the termination counter: the host only waits once per `blind` exchanges
     done = False
     iters = 0
     for _ in range(1 << 18):
         for _k in range(blind):
             # the first call settles the interior (dependency chains inside a crowded tile overlap run a few dozen deep);
             # afterwards only what hangs on halo states is left
-            engine.rounds(in_off, indeg, in_list, frozen, state, 32 if iters == 0 else 8, msg_remaining)
+            engine.rounds(in_off, indeg, in_list, frozen, state, 32 if iters == 0 else 4, msg_remaining)
             if nb:
                 torch.index_select(state, 0, band_pos, out=msg_band)
             _all_gather_flat(gathered, msg, world, group)
