@@ -41,21 +41,53 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
     }
 }
 
-__global__ void ccl_init_kernel(const float *__restrict__ mask, int64_t n, uint8_t *__restrict__ val, int *__restrict__ label) {
+// Labels start as the first pixel of the horizontal run inside the pixel's 32-pixel segment (one ballot): a run of equal
+// pixels is connected without a single atomic, and the union pass only has to stitch segment boundaries and the places where
+// a run meets a NEW run of the row above.  p % 32 == lane because the block size is a multiple of 32.
+__device__ __forceinline__ unsigned run_starts(bool start) { return __ballot_sync(0xffffffffu, start); }
+
+__global__ void __launch_bounds__(256) ccl_init_kernel(const float *__restrict__ mask, int64_t n, int W, uint8_t *__restrict__ val,
+                                                      int *__restrict__ label) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    val[p] = mask[p] != 0.f;
-    label[p] = (int)p;
+    const int lane = threadIdx.x & 31;
+    const bool in = p < n;
+    const int v = in ? (mask[p] != 0.f) : 0;
+    const int x = in ? (int)(p % W) : 0;
+    const bool start = !in || lane == 0 || x == 0 || ((mask[p - 1] != 0.f) != (v != 0));
+    const unsigned m = run_starts(start);
+    if (!in) return;
+    const int s = 31 - __clz(m & (0xffffffffu >> (31 - lane)));
+    val[p] = (uint8_t)v;
+    label[p] = (int)p - (lane - s);
 }
-// every pixel joins its left and upper neighbour of the same value (fg_only: background pixels stay singletons)
-__global__ void ccl_union_kernel(const uint8_t *__restrict__ val, int *__restrict__ label, int64_t n, int H, int W, int fg_only) {
+__global__ void __launch_bounds__(256) ccl_runs_kernel(const uint8_t *__restrict__ val, int64_t n, int W, int *__restrict__ label) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in = p < n;
+    const int v = in ? val[p] : 0;
+    const int x = in ? (int)(p % W) : 0;
+    const bool start = !in || lane == 0 || x == 0 || val[p - 1] != v;
+    const unsigned m = run_starts(start);
+    if (!in) return;
+    const int s = 31 - __clz(m & (0xffffffffu >> (31 - lane)));
+    label[p] = (int)p - (lane - s);
+}
+// stitches: the left neighbour across a segment boundary, and the upper neighbour unless the pixel's left neighbour already
+// made that connection (left and upper-left of the same value: p-1 ~ p-1-W by its own stitch, and both rows are runs)
+__global__ void __launch_bounds__(256) ccl_union_kernel(const uint8_t *__restrict__ val, int *__restrict__ label, int64_t n, int H,
+                                                       int W, int fg_only) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int v = val[p];
     if (fg_only && !v) return;
+    const int lane = threadIdx.x & 31;
     const int x = (int)(p % W), y = (int)((p / W) % H);
-    if (x > 0 && val[p - 1] == v) uf_union(label, (int)p, (int)p - 1);
-    if (y > 0 && val[p - W] == v) uf_union(label, (int)p, (int)p - W);
+    const bool left = x > 0 && val[p - 1] == v;
+    if (left && lane == 0) uf_union(label, (int)p, (int)p - 1);
+    if (y > 0 && val[p - W] == v) {
+        const bool covered = left && val[p - W - 1] == v;
+        if (!covered) uf_union(label, (int)p, (int)p - W);
+    }
 }
 __global__ void ccl_border_kernel(const uint8_t *__restrict__ val, int *__restrict__ label, int64_t n, int H, int W,
                                   uint8_t *__restrict__ open_bg) {
@@ -66,8 +98,8 @@ __global__ void ccl_border_kernel(const uint8_t *__restrict__ val, int *__restri
     const int x = (int)(p % W), y = (int)((p / W) % H);
     if (!val[p] && (x == 0 || y == 0 || x == W - 1 || y == H - 1)) open_bg[r] = 1;
 }
-// filled mask + reset of the labels and the per-root statistics for the second pass
-__global__ void ccl_fill_kernel(uint8_t *__restrict__ val, int *__restrict__ label, const uint8_t *__restrict__ open_bg, int64_t n,
+// filled mask + reset of the per-root statistics for the second pass
+__global__ void ccl_fill_kernel(uint8_t *__restrict__ val, const int *__restrict__ label, const uint8_t *__restrict__ open_bg, int64_t n,
                                 int *__restrict__ area, int *__restrict__ x0, int *__restrict__ y0, int *__restrict__ x1,
                                 int *__restrict__ y1) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -81,63 +113,111 @@ __global__ void ccl_fill_kernel(uint8_t *__restrict__ val, int *__restrict__ lab
     x1[p] = -1;
     y1[p] = -1;
 }
-__global__ void ccl_relabel_kernel(int *__restrict__ label, int64_t n) {
+// per-component area and box: one set of atomics per run segment (its first lane), not per pixel
+__global__ void __launch_bounds__(256) ccl_stats_kernel(const uint8_t *__restrict__ val, int *__restrict__ label, int64_t n, int H, int W,
+                                                       int *__restrict__ area, int *__restrict__ x0, int *__restrict__ y0,
+                                                       int *__restrict__ x1, int *__restrict__ y1) {
     const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p < n) label[p] = (int)p;
-}
-__global__ void ccl_stats_kernel(const uint8_t *__restrict__ val, int *__restrict__ label, int64_t n, int H, int W, int *__restrict__ area,
-                                 int *__restrict__ x0, int *__restrict__ y0, int *__restrict__ x1, int *__restrict__ y1) {
-    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n || !val[p]) return;
+    const int lane = threadIdx.x & 31;
+    const bool in = p < n;
+    const int v = in ? val[p] : 0;
+    const int x = in ? (int)(p % W) : 0;
+    const bool start = !in || lane == 0 || x == 0 || val[p - 1] != v;
+    const unsigned m = run_starts(start);
+    if (!in || !v) return;
     const int r = uf_find(label, (int)p);
     label[p] = r;
-    const int x = (int)(p % W), y = (int)((p / W) % H);
-    atomicAdd(area + r, 1);
+    if (!start) return;
+    const unsigned above = lane == 31 ? 0u : (m >> (lane + 1));
+    const int len = above ? __ffs(above) : 32 - lane;          // pixels of this run inside the segment (they are all in range)
+    const int y = (int)((p / W) % H);
+    atomicAdd(area + r, len);
     atomicMin(x0 + r, x);
+    atomicMax(x1 + r, x + len - 1);
     atomicMin(y0 + r, y);
-    atomicMax(x1 + r, x);
     atomicMax(y1 + r, y);
 }
-// one CTA per image: roots in raster order, area filter, rank by a running block scan
+// one CTA per image: component roots in raster order -> boxes.  Pass 1 counts the qualifying roots of every 32-pixel
+// segment, one block scan turns the counts into ranks, pass 2 writes.  kEmitSeg segments (32 K pixels... x32) per round.
+constexpr int kEmitSeg = 8192;
 __global__ void __launch_bounds__(1024) ccl_emit_kernel(const uint8_t *__restrict__ val, const int *__restrict__ label, int HW,
                                                         const int *__restrict__ area, const int *__restrict__ x0,
                                                         const int *__restrict__ y0, const int *__restrict__ x1,
                                                         const int *__restrict__ y1, int min_area, int max_area, int max_boxes,
                                                         float *__restrict__ boxes, int32_t *__restrict__ counts) {
+    __shared__ int s_cnt[kEmitSeg];
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t off = (int64_t)b * HW;
     if (tid == 0) s_base = 0;
     __syncthreads();
-    for (int p0 = 0; p0 < HW; p0 += 1024) {
-        const int p = p0 + tid;
-        bool take = false;
-        int64_t g = off + p;
-        if (p < HW && val[g] && label[g] == (int)g) {
-            const int ar = area[g];
-            take = ar > min_area && ar < max_area;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, take);
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        int before = __popc(m & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) before += s_warp[w];
-        const int rank = s_base + before;
-        if (take && rank < max_boxes) {
-            float *o = boxes + ((size_t)b * max_boxes + rank) * 5;
-            o[0] = (float)x0[g];
-            o[1] = (float)y0[g];
-            o[2] = (float)(x1[g] + 1);
-            o[3] = (float)(y1[g] + 1);
-            o[4] = 1.0f;
+    auto qualifies = [&](int p) {
+        if (p >= HW) return false;
+        const int64_t g = off + p;
+        if (!val[g] || label[g] != (int)g) return false;
+        const int ar = area[g];
+        return ar > min_area && ar < max_area;
+    };
+    for (int seg0 = 0; seg0 * 32 < HW; seg0 += kEmitSeg) {
+        const int nseg = min(kEmitSeg, (HW - seg0 * 32 + 31) / 32);
+        for (int sg = warp; sg < nseg; sg += 32) {
+            const unsigned m = __ballot_sync(0xffffffffu, qualifies((seg0 + sg) * 32 + lane));
+            if (lane == 0) s_cnt[sg] = __popc(m);
         }
         __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-            for (int w = 0; w < 32; ++w) t += s_warp[w];
-            s_base += t;
+        // exclusive scan of s_cnt[0..nseg): every thread owns a contiguous run of kEmitSeg / 1024 entries
+        constexpr int PER = kEmitSeg / 1024;
+        int loc[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int e = tid * PER + i;
+            loc[i] = e < nseg ? s_cnt[e] : 0;
+            sum += loc[i];
         }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        int run = s_base + s_warp[warp] + incl - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int e = tid * PER + i;
+            if (e < nseg) s_cnt[e] = run;
+            run += loc[i];
+        }
+        __syncthreads();
+        for (int sg = warp; sg < nseg; sg += 32) {
+            const int p = (seg0 + sg) * 32 + lane;
+            const bool take = qualifies(p);
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            const int rank = s_cnt[sg] + __popc(m & ((1u << lane) - 1u));
+            if (take && rank < max_boxes) {
+                const int64_t g = off + p;
+                float *o = boxes + ((size_t)b * max_boxes + rank) * 5;
+                o[0] = (float)x0[g];
+                o[1] = (float)y0[g];
+                o[2] = (float)(x1[g] + 1);
+                o[3] = (float)(y1[g] + 1);
+                o[4] = 1.0f;
+            }
+        }
+        __syncthreads();
+        if (tid == 1023) s_base = run;      // the last thread's running total = all roots so far
         __syncthreads();
     }
     if (tid == 0) counts[b] = s_base;
@@ -192,11 +272,11 @@ NUHTC_API int nuhtc_mask_components(const float *mask, int B, int H, int W, int 
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned nb = (unsigned)((n + 255) / 256);
     NUHTC_CUDA(cudaMemsetAsync(open_bg, 0, n, st));
-    ccl_init_kernel<<<nb, 256, 0, st>>>(mask, n, val, label);
+    ccl_init_kernel<<<nb, 256, 0, st>>>(mask, n, W, val, label);
     ccl_union_kernel<<<nb, 256, 0, st>>>(val, label, n, H, W, 0);
     ccl_border_kernel<<<nb, 256, 0, st>>>(val, label, n, H, W, open_bg);
     ccl_fill_kernel<<<nb, 256, 0, st>>>(val, label, open_bg, n, area, x0, y0, x1, y1);
-    ccl_relabel_kernel<<<nb, 256, 0, st>>>(label, n);
+    ccl_runs_kernel<<<nb, 256, 0, st>>>(val, n, W, label);
     ccl_union_kernel<<<nb, 256, 0, st>>>(val, label, n, H, W, 1);
     ccl_stats_kernel<<<nb, 256, 0, st>>>(val, label, n, H, W, area, x0, y0, x1, y1);
     ccl_emit_kernel<<<B, 1024, 0, st>>>(val, label, H * W, area, x0, y0, x1, y1, min_area, max_area, max_boxes, boxes, counts);

@@ -146,6 +146,17 @@ def main():
         rcfg = Cfg(nms_pre=1000, min_bbox_size=0, nms=dict(type="nms", iou_threshold=0.7), max_per_img=1000)
         ms, best = timeit(lambda: rpn.proposals_batched(cls, reg, anc, (512, 512, 3), rcfg), iters=5, warm=2)
         rec(f"rpn_proposals_batched_{B}img_nms_pre1000", ms, best, B * 4000 * 28, images_per_s=round(B / ms * 1e3))
+    if want("watershed"):
+        # watershed proposals (f4): 16 semantic maps at stride 4 of a 512 px frame -> instances of the hole-filled mask
+        from nuhtc_b200 import watershed as ws
+        g = torch.Generator().manual_seed(0)
+        sem = torch.nn.functional.interpolate(torch.randn(B, 1, 32, 32, generator=g), size=(128, 128), mode="bicubic").to(dev) * 3
+        m = ws.semantic_mask(sem, (512, 512), 0.0)
+        ms, best = timeit(lambda: ws.semantic_mask(sem, (512, 512), 0.0))
+        rec("watershed_semantic_mask_torch_16x512", ms, best, B * 512 * 512 * 4 * 2)
+        ms, best = timeit(lambda: ws.mask_components(m))
+        bx, cnt = ws.mask_components(m)
+        rec("watershed_components_16x512", ms, best, B * 512 * 512 * 5, instances=int(cnt.sum().item()))
     if want("merge"):
         d = synth.slide_nuclei(64, 64, per_tile=23, seed=0)
         xy, voff, sc = (torch.from_numpy(d[k]).to(dev) for k in ("xy", "voff", "score"))
