@@ -233,3 +233,38 @@ def test_strip_path_stress_sparse_repeated_concurrent(P):
     torch.cuda.synchronize()
     for name, o in res:
         assert (o - refs[name]).abs().max().item() <= TOL, name
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_shape_fuzz_default_path_vs_literal_kernel(seed):
+    """Random batch sizes, channel counts, frame sizes (odd map sizes, several x-strips or one), output sizes, sampling ratios
+    and box populations (nucleus-sized, map-sized, degenerate, partly or wholly outside the frame): the default path (strip
+    kernels + pipelined leftovers on the channel-group layout, or the NHWC / direct kernels where it does not apply) against the
+    literal per-sample kernel, which is bit-exact with the oracle (test_single_level_matches_oracle)."""
+    import nuhtc_b200 as nb
+    g = torch.Generator().manual_seed(1000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g).item())
+    B = ri(1, 5)
+    C = [32, 64, 96, 128, 256][ri(0, 4)]
+    frame = 32 * ri(3, 20)
+    strides = [4, 8, 16, 32]
+    feats = [torch.randn(B, C, max(1, frame // s), max(1, frame // s), generator=g).cuda() for s in strides]
+    P = [7, 14][ri(0, 1)]
+    sr = [0, 2][ri(0, 1)]
+    K = ri(1, 600)
+    ctr = torch.rand(K, 2, generator=g) * frame * 1.2 - frame * 0.1
+    kind = torch.rand(K, generator=g)
+    side = torch.where(kind < 0.6, 8 + torch.rand(K, generator=g) * 72,                       # nuclei
+                       torch.where(kind < 0.85, torch.exp(torch.rand(K, generator=g) * 4.2 + 2.3),   # 10 .. 660 px
+                                   torch.rand(K, generator=g) * 2.0))                         # degenerate
+    wh = side[:, None] * (0.5 + torch.rand(K, 2, generator=g))
+    rois = torch.cat([torch.randint(0, B, (K, 1), generator=g).float(), ctr - wh / 2, ctr + wh / 2], 1).cuda()
+    scales = [1.0 / s for s in strides]
+    for mode in ("route", "sum"):
+        lv = feats if mode == "route" else feats[:2]
+        sc = scales if mode == "route" else scales[:2]
+        a = nb.roi_align_levels(lv, rois, P, sc, sr, mode=mode)
+        b = nb.roi_align_levels(lv, rois, P, sc, sr, mode=mode, impl="direct")
+        tol = 1e-5 if mode == "route" else 2e-5
+        err = (a - b).abs().max().item()
+        assert err <= tol, (seed, mode, B, C, frame, P, sr, K, err)
