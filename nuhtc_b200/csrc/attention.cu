@@ -7,31 +7,43 @@
 // and adds to the pooled features.
 //
 // The reference gathers a [HW, C] copy of the level per unique cell.  Here a CTA owns 64 RoIs of one image and sweeps
-// the level once in tiles of 64 positions: S = Rn * F^T (register-tiled 64x64x64), the relu, then O += S * F
-// (second 64x64x64), i.e. the map is read once per 64 RoIs and S is never written to memory.  fp32 SIMT: the result must
+// the level once in tiles of 64 positions: S = Rn * F^T (register-tiled 64x64x64, 8x4 per thread), the relu, then
+// O += S * F (second 64x64x64), i.e. the map is read once per 64 RoIs and S is never written to memory.  fp32 SIMT: the result must
 // match the reference's fp32 CPU path to 1e-5, so no tensor cores / TF32.
 #include "common.cuh"
 
 namespace {
 
-constexpr int AR = 64;  // RoIs per CTA
-constexpr int AT = 32;  // positions per tile
-constexpr int APAD = 1; // row padding of the feature tile against bank conflicts
+constexpr int AR = 64;        // RoIs per CTA
+constexpr int AT = 64;        // positions per tile
+constexpr int ATH = 256;      // threads: 16 RoI groups (4 RoIs each) x 16 position / channel lanes
+constexpr int SF = 65;        // row stride of the feature tile (odd: the 16 lanes of a row group hit 16 banks)
+constexpr int SR = AR + 4;    // row stride of the transposed RoI-vector and similarity tiles (16-byte aligned rows)
 
-// rois sorted by image are not required: the CTA's 64 RoIs are taken from a per-image index list
-__global__ void __launch_bounds__(256) attn_pool_kernel(const float *__restrict__ feat, int H, int W, int C,
+// rois sorted by image are not required: the CTA's 64 RoIs are taken from a per-image index list.
+// Thread tile 4 RoIs x 4 positions (pass 1) / 4 RoIs x 4 channels (pass 2): 16 FMAs for 1 LDS.128 + 4 LDS.32.  The grid is
+// compact (one CTA per 64 RoIs of an image, found through the per-image counts): round 1 launched ceil(K/64) x B CTAs of
+// which 1 in 16 had work, and the working ones landed on the SMs in clumps (ncu: SMSPs active 54 % of the kernel's time).
+// The accumulation orders (channels ascending in pass 1, positions ascending in pass 2) are unchanged, so are the results.
+__global__ void __launch_bounds__(ATH) attn_pool_kernel(const float *__restrict__ feat, int H, int W, int C,
                                                         const float *__restrict__ rois, const int32_t *__restrict__ order,
-                                                        const int32_t *__restrict__ img_start, float inv_stride2, float thres,
+                                                        const int32_t *__restrict__ img_start, int B, float inv_stride2, float thres,
                                                         int accumulate, float *__restrict__ out) {
     // C == 64 in every NuHTC config; the kernel is written for C <= 64 (channels beyond C are zero padded)
-    __shared__ float s_r[AR][64];         // normalised RoI vectors (read as warp broadcasts)
-    __shared__ float s_f[AT][64 + APAD];  // raw features of the tile
-    __shared__ float s_s[AR][AT];         // similarities of the tile
-    __shared__ float s_inv[AT];           // 1 / max(||f_p||, eps)
-    const int b = blockIdx.y;
+    extern __shared__ __align__(16) float attn_smem[];
+    float (*s_rT)[SR] = reinterpret_cast<float (*)[SR]>(attn_smem);                      // normalised RoI vectors, [channel][roi]
+    float (*s_sT)[SR] = reinterpret_cast<float (*)[SR]>(attn_smem + 64 * SR);            // similarities of the tile, [position][roi]
+    float (*s_f)[SF] = reinterpret_cast<float (*)[SF]>(attn_smem + 64 * SR + AT * SR);   // raw features of the tile, [position][channel]
+    float *s_inv = attn_smem + 64 * SR + AT * SR + AT * SF;                              // 1 / max(||f_p||, eps)
+    int b = 0, u = blockIdx.x;
+    for (; b < B; ++b) {   // CTA u of the compact grid -> (image, first RoI)
+        const int nb = (img_start[b + 1] - img_start[b] + AR - 1) / AR;
+        if (u < nb) break;
+        u -= nb;
+    }
+    if (b == B) return;
     const int n_img = img_start[b + 1] - img_start[b];
-    const int r0 = blockIdx.x * AR;
-    if (r0 >= n_img) return;
+    const int r0 = u * AR;
     const int nr = min(AR, n_img - r0);
     const int tid = threadIdx.x;
     const int HW = H * W;
@@ -39,7 +51,7 @@ __global__ void __launch_bounds__(256) attn_pool_kernel(const float *__restrict_
     const float eps = 1e-8f;
 
     // ---- RoI vectors: feature at the centre cell, normalised
-    for (int i = tid; i < AR * 64; i += 256) {
+    for (int i = tid; i < AR * 64; i += ATH) {
         const int r = i >> 6, c = i & 63;
         float v = 0.f;
         if (r < nr && c < C) {
@@ -51,18 +63,16 @@ __global__ void __launch_bounds__(256) attn_pool_kernel(const float *__restrict_
             cy = min(max(cy, 0), H - 1);
             v = __ldg(fb + ((size_t)cy * W + cx) * C + c);
         }
-        s_r[r][c] = v;
+        s_rT[c][r] = v;
     }
     __syncthreads();
     if (tid < AR) {
         float n2 = 0.f;
-        for (int c = 0; c < 64; ++c) n2 += s_r[tid][c] * s_r[tid][c];
+        for (int c = 0; c < 64; ++c) n2 += s_rT[c][tid] * s_rT[c][tid];
         const float inv = 1.0f / fmaxf(sqrtf(n2), eps);
-        for (int c = 0; c < 64; ++c) s_r[tid][c] *= inv;
+        for (int c = 0; c < 64; ++c) s_rT[c][tid] *= inv;
     }
-    // thread tile: 4 RoIs x (2 positions in pass 1 | 4 channels in pass 2); columns are interleaved by 16 so that the 16
-    // lanes sharing a row group touch consecutive shared-memory rows / words (conflict free)
-    const int tr = (tid >> 4) * 4, tl = tid & 15;
+    const int tr = (tid >> 4) * 4, tl = tid & 15;   // RoIs tr..tr+3; positions / channels tl, tl+16, tl+32, tl+48
     float o[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -70,10 +80,29 @@ __global__ void __launch_bounds__(256) attn_pool_kernel(const float *__restrict_
         for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
 
     for (int p0 = 0; p0 < HW; p0 += AT) {
-        __syncthreads(); // previous tile fully consumed (also orders the s_r normalisation before its first use)
-        for (int i = tid; i < AT * 64; i += 256) {
-            const int p = i >> 6, c = i & 63;
-            s_f[p][c] = (p0 + p < HW && c < C) ? __ldg(fb + (size_t)(p0 + p) * C + c) : 0.f;
+        __syncthreads(); // previous tile fully consumed (also orders the s_rT normalisation before its first use)
+        if (C == 64) {
+            // all 8 loads of a thread are in flight together (a rolled loop of dependent load -> store pairs cost one L2
+            // round trip per element: 19 k cycles per tile, most of the kernel's time before this was unrolled)
+            float4 v[AT * 16 / ATH];
+#pragma unroll
+            for (int u = 0; u < AT * 16 / ATH; ++u) {
+                const int i4 = tid + u * ATH, p = i4 >> 4, c4 = (i4 & 15) * 4;
+                v[u] = p0 + p < HW ? __ldg(reinterpret_cast<const float4 *>(fb + (size_t)(p0 + p) * 64 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < AT * 16 / ATH; ++u) {
+                const int i4 = tid + u * ATH, p = i4 >> 4, c4 = (i4 & 15) * 4;
+                s_f[p][c4] = v[u].x;
+                s_f[p][c4 + 1] = v[u].y;
+                s_f[p][c4 + 2] = v[u].z;
+                s_f[p][c4 + 3] = v[u].w;
+            }
+        } else {
+            for (int i = tid; i < AT * 64; i += ATH) {
+                const int p = i >> 6, c = i & 63;
+                s_f[p][c] = (p0 + p < HW && c < C) ? __ldg(fb + (size_t)(p0 + p) * C + c) : 0.f;
+            }
         }
         __syncthreads();
         if (tid < AT) {
@@ -83,38 +112,43 @@ __global__ void __launch_bounds__(256) attn_pool_kernel(const float *__restrict_
         }
         __syncthreads();
         // pass 1: S[r][p] = relu(<Rn[r], F[p]> * inv[p] - thres) + thres
-        float s[4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < 64; ++c) {
-            float a[4], f[2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = s_r[tr + i][c];
-            f[0] = s_f[tl][c];
-            f[1] = s_f[tl + 16][c];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                s[i][0] = fmaf(a[i], f[0], s[i][0]);
-                s[i][1] = fmaf(a[i], f[1], s[i][1]);
-            }
-        }
+        float s[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int p = tl + 16 * j;
-                const bool live = p0 + p < HW;
-                const float cosv = s[i][j] * s_inv[p];
-                s_s[tr + i][p] = live ? fmaxf(cosv - thres, 0.f) + thres : 0.f;
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < 64; ++c) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&s_rT[c][tr]);
+            const float a[4] = {a0.x, a0.y, a0.z, a0.w};
+            float f[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = s_f[tl + 16 * j][c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = fmaf(a[i], f[j], s[i][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = tl + 16 * j;
+            const bool live = p0 + p < HW;
+            const float inv = s_inv[p];
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float cosv = s[i][j] * inv;
+                v[i] = live ? fmaxf(cosv - thres, 0.f) + thres : 0.f;
             }
+            *reinterpret_cast<float4 *>(&s_sT[p][tr]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
         __syncthreads();
         // pass 2: O[r][c] += sum_p S[r][p] * F[p][c]
 #pragma unroll 8
         for (int p = 0; p < AT; ++p) {
-            float a[4], f[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = s_s[tr + i][p];
+            const float4 a0 = *reinterpret_cast<const float4 *>(&s_sT[p][tr]);
+            const float a[4] = {a0.x, a0.y, a0.z, a0.w};
+            float f[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) f[j] = s_f[p][tl + 16 * j];
 #pragma unroll
@@ -201,8 +235,14 @@ NUHTC_API int nuhtc_attention_pool(const float *feat_nhwc, int B, int H, int W, 
     attn_scan_kernel<<<1, 32, 0, st>>>(cnt, B, img_start);
     NUHTC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (B + 1), st)); // reused as the fill cursors
     attn_fill_kernel<<<(K + 255) / 256, 256, 0, st>>>(rois, K, B, img_start, cnt, order);
-    dim3 grid((K + AR - 1) / AR, B); // upper bound per image; CTAs beyond an image's RoI count exit at once
-    attn_pool_kernel<<<grid, 256, 0, st>>>(feat_nhwc, H, W, C, rois, order, img_start, 1.0f / (2.0f * stride), thres, accumulate, out);
+    const unsigned grid = (unsigned)((K + AR - 1) / AR + B);   // >= sum over images of ceil(n_b / AR); the few spare CTAs exit at once
+    constexpr size_t smem = sizeof(float) * (64 * SR + AT * SR + AT * SF + AT);
+    static bool attr_done[kNuhtcMaxDevices] = {false};
+    if (!attr_done[nuhtc_device()]) {
+        NUHTC_CUDA(cudaFuncSetAttribute(attn_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[nuhtc_device()] = true;
+    }
+    attn_pool_kernel<<<grid, ATH, smem, st>>>(feat_nhwc, H, W, C, rois, order, img_start, B, 1.0f / (2.0f * stride), thres, accumulate, out);
     NUHTC_LAUNCH_CHECK();
     return NUHTC_OK;
 }

@@ -42,7 +42,7 @@ def main():
     if len(src) > 2 and "Instructions Executed" in src[1]:
         h = src[1]
         ia, isamp, isrc = h.index("Instructions Executed"), h.index("# Samples"), h.index("Source")
-        data = src[2:]
+        data = [r for r in src[2:] if len(r) > max(ia, isamp, isrc) and r[ia].strip().isdigit() and r[isamp].strip().isdigit()]   # a report with several kernels repeats the header rows
         ti = sum(int(r[ia]) for r in data) or 1
         ts = sum(int(r[isamp]) for r in data) or 1
         c, cs = Counter(), Counter()
