@@ -870,16 +870,8 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
                 const uint32_t col0 = smem_u32(s_ring) + (uint32_t)((xoff * kCG + 4 * q) * 4);
                 const uint32_t wyd0 = smem_u32(&R.wyd[0][0]);
                 // GRP bit g: bins 4g .. 4g+3
-                auto rows = [&](auto NXC, auto GRPC, int j0, int r0, int r1_) {
+                auto rows = [&](auto NXC, auto GRPC, const float *wx, const int *toff, int r0, int r1_) {
                     constexpr int NX = decltype(NXC)::value, GRP = decltype(GRPC)::value;
-                    float wx[NX];
-                    int toff[NX];
-#pragma unroll
-                    for (int j = 0; j < NX; ++j) {
-                        const bool ok = j0 + j < nx;
-                        wx[j] = ok ? wxp[j0 + j] : 0.f;
-                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG * 4;   // a padded tap repeats the lane's own last cell
-                    }
                     unsigned sl = slot0 + r0;
                     if (sl >= NR) sl -= NR;
                     uint32_t rowp = col0 + sl * (uint32_t)(kRowFloats * 4);
@@ -918,18 +910,27 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
                     }
                 };
                 auto sweep = [&](auto NXC, int j0) {
+                    constexpr int NX = decltype(NXC)::value;
+                    float wx[NX];   // the x taps of this pass: set up once, shared by the (up to seven) row stretches
+                    int toff[NX];
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) {
+                        const bool ok = j0 + j < nx;
+                        wx[j] = ok ? wxp[j0 + j] : 0.f;
+                        toff[j] = (ok ? j0 + j : (nx > 0 ? nx - 1 : 0)) * kCG * 4;   // a padded tap repeats the lane's own last cell
+                    }
                     if (R.gdense) {   // a row feeds three groups (very small RoIs): every row feeds every bin
-                        rows(NXC, std::integral_constant<int, 15>{}, j0, 0, hh);
+                        rows(NXC, std::integral_constant<int, 15>{}, wx, toff, 0, hh);
                         return;
                     }
                     const int s1 = R.gs[1], s2 = R.gs[2], s3 = R.gs[3], e0 = R.ge[0], e1 = R.ge[1], e2 = R.ge[2];
-                    rows(NXC, std::integral_constant<int, 1>{}, j0, 0, min(e0, s1));
-                    rows(NXC, std::integral_constant<int, 3>{}, j0, s1, e0);
-                    rows(NXC, std::integral_constant<int, 2>{}, j0, max(e0, s1), min(e1, s2));
-                    rows(NXC, std::integral_constant<int, 6>{}, j0, s2, e1);
-                    rows(NXC, std::integral_constant<int, 4>{}, j0, max(e1, s2), min(e2, s3));
-                    rows(NXC, std::integral_constant<int, 12>{}, j0, s3, e2);
-                    rows(NXC, std::integral_constant<int, 8>{}, j0, max(e2, s3), hh);
+                    rows(NXC, std::integral_constant<int, 1>{}, wx, toff, 0, min(e0, s1));
+                    rows(NXC, std::integral_constant<int, 3>{}, wx, toff, s1, e0);
+                    rows(NXC, std::integral_constant<int, 2>{}, wx, toff, max(e0, s1), min(e1, s2));
+                    rows(NXC, std::integral_constant<int, 6>{}, wx, toff, s2, e1);
+                    rows(NXC, std::integral_constant<int, 4>{}, wx, toff, max(e1, s2), min(e2, s3));
+                    rows(NXC, std::integral_constant<int, 12>{}, wx, toff, s3, e2);
+                    rows(NXC, std::integral_constant<int, 8>{}, wx, toff, max(e2, s3), hh);
                 };
 #pragma unroll 1
                 for (int j0 = 0; j0 < nxu; j0 += 4) {   // one call site: the sweep code exists once
