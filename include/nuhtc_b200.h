@@ -210,6 +210,9 @@ int nuhtc_merge(const double *xy, const int64_t *voff, const double *score, int6
 int nuhtc_merge_graph(const double *xy, const int64_t *voff, const double *score, int64_t N, int64_t sumV,
                       double thr, int64_t max_pairs, int32_t *indeg, int32_t *in_off, int32_t *in_list,
                       int64_t *num_pairs, int32_t *status, void *ws, size_t ws_bytes, void *stream);
+/* y extent (min, max of the vertex y coordinates) of every ring: what `seam.merge_distributed` compares with the stripe
+ * extents of the other ranks to find the nuclei that have to travel. */
+int nuhtc_ring_yextent(const double *xy, const int64_t *voff, int64_t N, double *ymin, double *ymax, void *stream);
 int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_t *in_list, int64_t N,
                        const uint8_t *frozen, uint8_t *state, int64_t *remaining, int rounds, void *stream);
 

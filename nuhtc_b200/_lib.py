@@ -58,6 +58,7 @@ SIGNATURES = {
     "nuhtc_rpn_topk_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp, _vp]),
     "nuhtc_mask_components_workspace_bytes": (_c.c_size_t, [_i, _i, _i]),
     "nuhtc_mask_components": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _c.c_size_t, _vp]),
+    "nuhtc_ring_yextent": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "nuhtc_keep_flags": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp]),
 }
 

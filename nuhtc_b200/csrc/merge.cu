@@ -529,6 +529,33 @@ NUHTC_API int nuhtc_merge_graph(const double *xy, const int64_t *voff, const dou
     return build_graph(L, xy, voff, score, N, thr, max_pairs, indeg, in_off, in_list, num_pairs, status, st);
 }
 
+namespace {
+// y extent of every ring (the multi-GPU merge classifies nuclei against the stripe extents with it): one thread per ring
+__global__ void ring_yextent_kernel(const double *__restrict__ xy, const int64_t *__restrict__ voff, int64_t N,
+                                    double *__restrict__ ymin, double *__restrict__ ymax) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double lo = 1e300, hi = -1e300;
+    for (int64_t v = voff[i]; v < voff[i + 1]; ++v) {
+        const double y = xy[2 * v + 1];
+        lo = fmin(lo, y);
+        hi = fmax(hi, y);
+    }
+    ymin[i] = lo;
+    ymax[i] = hi;
+}
+
+} // namespace
+
+NUHTC_API int nuhtc_ring_yextent(const double *xy, const int64_t *voff, int64_t N, double *ymin, double *ymax, void *stream) {
+    NUHTC_CHECK_ARG(N >= 0, "ring_yextent: bad size");
+    if (N == 0) return NUHTC_OK;
+    NUHTC_CHECK_ARG(xy && voff && ymin && ymax, "ring_yextent: null pointer");
+    ring_yextent_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(xy, voff, N, ymin, ymax);
+    NUHTC_LAUNCH_CHECK();
+    return NUHTC_OK;
+}
+
 NUHTC_API int nuhtc_merge_rounds(const int32_t *in_off, const int32_t *indeg, const int32_t *in_list, int64_t N,
                                  const uint8_t *frozen, uint8_t *state, int64_t *remaining, int rounds, void *stream) {
     NUHTC_CHECK_ARG(N >= 0 && rounds >= 1, "merge_rounds: bad sizes");

@@ -62,6 +62,15 @@ class CudaMergeEngine:
             return indeg[:N], in_off, in_list
         raise L.NuhtcError("merge_graph: candidate-pair capacity could not be satisfied")
 
+    def yextent(self, xy: torch.Tensor, voff: torch.Tensor):
+        N = voff.numel() - 1
+        ymin = torch.empty(N, dtype=torch.float64, device=xy.device)
+        ymax = torch.empty(N, dtype=torch.float64, device=xy.device)
+        with torch.cuda.device(xy.device):
+            rc = L.lib().nuhtc_ring_yextent(xy.data_ptr(), voff.data_ptr(), N, ymin.data_ptr(), ymax.data_ptr(), L.stream_ptr(xy.device))
+        L.check(rc, "ring_yextent")
+        return ymin, ymax
+
     def rounds(self, in_off, indeg, in_list, frozen, state, nrounds: int, remaining: Optional[torch.Tensor] = None) -> torch.Tensor:
         dev = state.device
         if remaining is None:
@@ -236,9 +245,12 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
     N = score.numel()
     gid = torch.as_tensor(shard["gid"], dtype=torch.int64, device=dev)
     cnt = voff[1:] - voff[:-1]
-    ycol = xy[:, 1].contiguous()
-    ymin = torch.segment_reduce(ycol, "min", lengths=cnt, unsafe=True)     # per-nucleus y extent: one segmented pass each
-    ymax = torch.segment_reduce(ycol, "max", lengths=cnt, unsafe=True)
+    if hasattr(engine, "yextent"):
+        ymin, ymax = engine.yextent(xy.contiguous(), voff)                      # one launch (torch.segment_reduce: 2 x 160 us at 100 k rings)
+    else:
+        ycol = xy[:, 1].contiguous()
+        ymin = torch.segment_reduce(ycol, "min", lengths=cnt, unsafe=True)
+        ymax = torch.segment_reduce(ycol, "max", lengths=cnt, unsafe=True)
     extents = [stripe_extent(shard, stripe_rows(shard["tiles_y"], q, world)) for q in range(world)]
 
     # ---- band = own nuclei that reach into another rank's stripe
@@ -355,7 +367,7 @@ def merge_distributed(xy: torch.Tensor, voff: torch.Tensor, score: torch.Tensor,
         for _k in range(blind):
             # the first call settles the interior (dependency chains inside a crowded tile overlap run a few dozen deep);
             # afterwards only what hangs on halo states is left
-            engine.rounds(in_off, indeg, in_list, frozen, state, 32 if iters == 0 else 4, msg_remaining)
+            engine.rounds(in_off, indeg, in_list, frozen, state, 16 if iters == 0 else 4, msg_remaining)
             if nb:
                 torch.index_select(state, 0, band_pos, out=msg_band)
             _all_gather_flat(gathered, msg, world, group)
