@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(1024) strip_scan_kernel(StripArgs a) {
         s_units = 0;
     }
     __syncthreads();
+    extern __shared__ int s_h[];
     {   // the histogram is staged in shared memory (coalesced both ways); every thread owns a contiguous run of keys:
         // local sum, one block scan of the 1024 partial sums, local write-back
-        extern __shared__ int s_h[];
         for (int i = tid; i < a.nkeys; i += 1024) s_h[i] = a.hist[i];
         __syncthreads();
         const int per = (a.nkeys + 1023) / 1024;
@@ -239,11 +239,15 @@ __global__ void __launch_bounds__(1024) strip_scan_kernel(StripArgs a) {
             b = bs / lv.nstrips;
             const int ka = lv.key0 + bs * lv.H + yp * lv.ypart_rows;
             const int kb = lv.key0 + bs * lv.H + min(lv.H, (yp + 1) * lv.ypart_rows);
-            begin = a.hist[ka];
-            cnt = a.hist[kb] - begin;
+            // the scanned histogram is still in shared memory (entry nkeys = the total): the walk below is a chain of
+            // dependent reads, 32 L2 round trips per bin when it went through a.hist
+            const int total = s_carry;
+            auto Hs = [&](int i) { return i < a.nkeys ? s_h[i] : total; };
+            begin = Hs(ka);
+            cnt = Hs(kb) - begin;
             if (cnt > 0) {
                 int kk = ka;
-                while (a.hist[kk + 1] == begin) ++kk;   // first non-empty key of the bin = smallest window top
+                while (Hs(kk + 1) == begin) ++kk;   // first non-empty key of the bin = smallest window top
                 Y0 = kk - (lv.key0 + bs * lv.H);
             }
         }
@@ -748,7 +752,7 @@ static size_t strip7_smem_bytes() {
 // thread = (channel quad q < 8, output column pw < 14): 112 threads, 4 channels each; a quarter-warp reads the 8 quads of
 // ONE cell (128 contiguous bytes), so the tap loads are conflict-free.  Same row-major sweep as the 7x7 kernel with four
 // bin groups (0-3, 4-7, 8-11, 12-13): a row feeds one group or two neighbouring ones, which gives seven counted loops.
-// The [32][14][14] result leaves in two 16-channel phases through the team tile (12.5 KB), one bulk store each.
+// The [32][14][14] result leaves in ONE pass through the team tile (25 KB) and one bulk store (see the flush).
 struct Strip14Cfg {
     static constexpr int NT = 3, TW = 4, TEAM = TW * 32;
     static constexpr int NTHREADS = 32 + NT * TEAM;
@@ -803,8 +807,6 @@ __global__ void __launch_bounds__(Strip14Cfg::NTHREADS, 1) roi_align_strip14_ker
     const uint32_t rf0 = B.rfull0 + 8 * (team * 2);
     const int bar_id = 1 + team;
     auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TEAM) : "memory"); };
-    // tile write: the four channels of a thread are written in an order rotated by q/2 (784*q = 16*q mod 32: without the
-    // rotation the quads of a phase would pile onto two bank groups)
     const bool r2 = (q & 2) != 0;   // quads 2,3 of a flush phase (see the flush)
     unsigned rec_uses[2] = {0u, 0u};
     bool store_pending = false;
