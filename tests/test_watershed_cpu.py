@@ -46,3 +46,14 @@ def test_instances_edge_cases(oracle):
     d[7:12, 7:12] = 1                                    # touches the first one only diagonally: two instances (4-connectivity)
     b = oracle.watershed_instances(d)[0]
     assert b.tolist() == [[2, 2, 7, 7, 1], [7, 7, 12, 12, 1]]
+
+
+def test_product_torch_half_matches_golden_mask_on_cpu():
+    """The device half of the product (upsample, blur, threshold, opening) is plain torch and also runs on CPU tensors: it must
+    reproduce the mask the reference's code produced for the golden input.  (The component half has no CPU path.)"""
+    from nuhtc_b200.watershed import semantic_mask, mask_components
+    z = np.load(G)
+    m = semantic_mask(torch.from_numpy(z["semantic_pred"]), (256, 256), 0.0)
+    assert np.array_equal(m[:, 0].numpy().astype(np.uint8), z["mask"])
+    with pytest.raises(Exception):
+        mask_components(m)
