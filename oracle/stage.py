@@ -70,5 +70,5 @@ def roi_stage_cpu(feats: Sequence[torch.Tensor], rois: torch.Tensor, bbox_heads:
         mk = masks.numpy().astype(np.uint8)
         contours = [O.mask2inst(mk[int(i)]) for i in keep]
         out.append(dict(det_boxes=det_boxes, det_scores=dets[:, 4], det_labels=labels, det_cand=det_cand, masks=masks, keep=keep,
-                        contours=contours))
+                        contours=contours, mask_prob=logits.sigmoid()))
     return out

@@ -103,8 +103,15 @@ def test_stage_end_to_end_vs_reference_flow(oracle):
         assert len(sel) == r["det_boxes"].shape[0]
         assert (res.det_boxes.cpu()[sel] - r["det_boxes"]).abs().max().item() <= 1e-3
         assert torch.equal(res.det_labels.cpu()[sel], r["det_labels"])
-        same = (res.masks.cpu()[sel] == r["masks"]).float().mean().item()
-        assert same > 0.9999
+        # masks: the two flows paste through boxes that differ by up to 1e-3 px (GPU vs CPU head GEMMs, three decodes deep), so
+        # a pixel may only disagree where the reference's pasted probability is within that displacement's reach of the
+        # threshold: 1e-3 px of a ~40 px box = 7e-4 of a 28-px map cell at <= 0.25 probability per cell -> 2e-4; bound 1e-3
+        diff = res.masks.cpu()[sel] != r["masks"]
+        if diff.any():
+            H, W = r["masks"].shape[1:]
+            prob = oracle.paste_masks(r["mask_prob"], r["det_boxes"], H, W)
+            assert ((prob - 0.5).abs()[diff] <= 1e-3).all()
+        assert diff.float().mean().item() < 1e-4
         got = set((kept[b].cpu().numpy() - sel[0]).tolist())
         assert got == set(r["keep"].tolist())
 
