@@ -67,22 +67,85 @@ def mask_nms_device(bits: torch.Tensor, area: torch.Tensor, bbox: torch.Tensor, 
     return keep, tstart, tcount, status
 
 
-def rle_encode(mask: np.ndarray) -> dict:
-    """pycocotools-compatible uncompressed RLE of one [h,w] mask (column-major runs), host side.
-    The reference's compressed byte string needs pycocotools; consumers that only need counts/area can use this."""
-    h, w = mask.shape
+def _runs(mask: np.ndarray) -> np.ndarray:
+    """Column-major run lengths of one [h,w] mask, starting with a run of zeros (possibly empty): pycocotools rleEncode."""
     flat = np.asarray(mask, dtype=bool).T.reshape(-1)
     change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
     edges = np.concatenate([[0], change, [flat.size]])
     runs = np.diff(edges)
     if flat.size and flat[0]:
         runs = np.concatenate([[0], runs])
-    return {"size": [h, w], "counts": runs.astype(np.uint32).tolist()}
+    return runs.astype(np.int64)
+
+
+def rle_counts_to_string(counts) -> bytes:
+    """pycocotools' compressed `counts` (common/maskApi.c rleToString): every count from the fourth on is stored as its
+    difference to the count two places back, each value in little-endian groups of 5 bits + a continuation bit, as ASCII
+    characters 48..111."""
+    out = bytearray()
+    cnts = [int(c) for c in counts]
+    for i, x in enumerate(cnts):
+        if i > 2:
+            x -= cnts[i - 2]
+        more = True
+        while more:
+            c = x & 0x1F
+            x >>= 5                                  # arithmetic shift: negative differences end on x == -1
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(c + 48)
+    return bytes(out)
+
+
+def rle_string_to_counts(s: bytes) -> List[int]:
+    """Inverse of rle_counts_to_string (maskApi.c rleFrString)."""
+    cnts: List[int] = []
+    p = 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = s[p] - 48
+            x |= (c & 0x1F) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1
+            k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(cnts) > 2:
+            x += cnts[-2]
+        cnts.append(x)
+    return cnts
+
+
+def rle_encode(mask: np.ndarray, compressed: bool = True) -> dict:
+    """`maskUtils.encode(np.asfortranarray(mask))` for one [h,w] mask on the host: {'size': [h, w], 'counts': bytes}
+    (compressed=False: the run lengths as a list, pycocotools' "uncompressed RLE")."""
+    h, w = mask.shape
+    runs = _runs(mask)
+    return {"size": [h, w], "counts": rle_counts_to_string(runs) if compressed else runs.tolist()}
+
+
+def rle_decode(rle: dict) -> np.ndarray:
+    """`maskUtils.decode` of one RLE dict -> [h,w] uint8."""
+    h, w = rle["size"]
+    counts = rle["counts"]
+    if isinstance(counts, (bytes, str)):
+        counts = rle_string_to_counts(counts.encode() if isinstance(counts, str) else counts)
+    flat = np.zeros(h * w, dtype=np.uint8)
+    pos, v = 0, 0
+    for c in counts:
+        if v:
+            flat[pos:pos + c] = 1
+        pos += c
+        v ^= 1
+    return flat.reshape(w, h).T.copy()
 
 
 def mask_nms(masks, pred_scores, thr: float = 0.9, min_area=None) -> Tuple[List[dict], np.ndarray]:
     """Same call as the reference: ``masks`` is a list/array of [h,w] uint8 masks (host or CUDA),
-    ``pred_scores`` their scores.  Returns (kept masks as RLE dicts, kept indices in score order)."""
+    ``pred_scores`` their scores.  Returns (kept masks as pycocotools RLE dicts with compressed `counts`, kept indices in
+    score order)."""
     if isinstance(masks, torch.Tensor):
         m = masks
     else:

@@ -17,9 +17,9 @@ def test_rle_encode_matches_oracle_runs(oracle):
         cnts = np.zeros(m.size + 1, dtype=np.uint32)
         k = oracle.lib().oracle_rle_encode(m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), 17, 23,
                                            cnts.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
-        assert rle_encode(m)["counts"] == cnts[:k].tolist()
-    assert rle_encode(np.zeros((4, 4), np.uint8))["counts"] == [16]
-    assert rle_encode(np.ones((4, 4), np.uint8))["counts"] == [0, 16]
+        assert rle_encode(m, compressed=False)["counts"] == cnts[:k].tolist()
+    assert rle_encode(np.zeros((4, 4), np.uint8), compressed=False)["counts"] == [16]
+    assert rle_encode(np.ones((4, 4), np.uint8), compressed=False)["counts"] == [0, 16]
 
 
 def test_features_to_arrays_and_cli():
@@ -88,3 +88,23 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["metric"] == "wsi_tiles_per_sec_roi_stage_plus_merge" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_compressed_rle_string_round_trip():
+    """The `counts` byte string of pycocotools (maskApi.c rleToString / rleFrString): 6-bit groups as ASCII 48..111, counts from
+    the fourth on stored as differences to the count two places back (negative differences included)."""
+    from nuhtc_b200.mask_nms import rle_counts_to_string, rle_decode, rle_string_to_counts
+    assert rle_counts_to_string([5]) == b"5"                       # 5 -> one group, no continuation
+    assert rle_counts_to_string([31]) == b"o0"                     # 31 = 0b11111: bit 4 set -> continuation flag + an empty group
+    assert rle_counts_to_string([0, 16]) == b"0`0"                 # 16 -> group 16|32 then 0
+    for counts in ([10, 3, 200, 1, 7, 100000, 2], [0, 1, 1, 1, 1, 1], [7, 300, 2, 5, 1000, 1, 3, 900]):
+        s = rle_counts_to_string(counts)
+        assert all(48 <= c <= 111 for c in s)
+        assert rle_string_to_counts(s) == counts
+    g = np.random.default_rng(0)
+    for t in range(100):
+        h, w = int(g.integers(1, 70)), int(g.integers(1, 70))
+        m = (g.random((h, w)) < g.random()).astype(np.uint8)
+        r = rle_encode(m)
+        assert isinstance(r["counts"], bytes) and r["size"] == [h, w]
+        assert np.array_equal(rle_decode(r), m)

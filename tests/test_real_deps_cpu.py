@@ -35,6 +35,9 @@ def test_pycocotools_rle_iou(oracle):
     rles = [mu.encode(np.asfortranarray(m)) for m in masks]
     ref = mu.iou(rles, rles, [0] * len(rles))
     assert np.array_equal(oracle.mask_iou(masks), ref)          # integer pixel counts, one double division
+    from nuhtc_b200.mask_nms import rle_encode
+    for m, r in zip(masks, rles):
+        assert rle_encode(m) == {"size": list(r["size"]), "counts": r["counts"]}      # the compressed byte string itself
 
 
 def test_shapely_polygon_iou_and_merge(oracle):
